@@ -245,5 +245,27 @@ def main():
     save('ties_2000', rec)
 
 
+def api_surface():
+    """public names of the reference package and the methods bound on the four layouts"""
+    skip = {'Any', 'List', 'Tuple', 'Union', 'Number', 'NamedTuple', 'Tensor', 'PackedSequence', 'torch', 'Key',
+            'Value'}
+    names = sorted(n for n in dir(rua) if not n.startswith('_') and n not in skip
+                   and not isinstance(getattr(rua, n), type(os)))
+    with open(os.path.join(OUT, 'api_names.txt'), 'w') as fp:
+        fp.write('\n'.join(names) + '\n')
+    lines = []
+    for k, cls in KINDS.items():
+        for m in sorted(dir(cls)):
+            if m.startswith('_') or m in ('count', 'index'):
+                continue
+            if k == 'P' and m in dir(tuple):
+                continue
+            lines.append(f'{k} {m}')
+    with open(os.path.join(OUT, 'api_methods.txt'), 'w') as fp:
+        fp.write('\n'.join(lines) + '\n')
+    print(f'api: {len(names)} names, {len(lines)} methods')
+
+
 if __name__ == '__main__':
     main()
+    api_surface()

@@ -1,0 +1,472 @@
+"""Tensor-level wrappers over the C-ABI: validate -> allocate outputs with torch -> call ``rua_*`` with raw
+pointers on the current CUDA stream -> wrap the result.  torch is plumbing here (device memory,
+streams, autograd graph); every byte of the hot path is moved or reduced by librua_b200.so.
+
+No CPU path exists: non-CUDA tensors raise ``RuntimeError``.
+"""
+import ctypes
+import weakref
+from dataclasses import dataclass, field
+from typing import Optional, Tuple
+
+import torch
+from torch import Tensor
+
+from torchrua_b200 import _lib
+from torchrua_b200._lib import (CAT, LEFT, LEN_CONST, LEN_MINUS, LEN_SAME, MAP_REV, MAP_ROLL, MAP_SHIFT, PACK,
+                                PAD_FILL, PAD_ROW0, RIGHT)
+
+_DTYPES = {torch.float32: _lib.F32, torch.float64: _lib.F64, torch.float16: _lib.F16, torch.bfloat16: _lib.BF16}
+_OPS = {'sum': _lib.SUM, 'mean': _lib.MEAN, 'prod': _lib.PROD, 'max': _lib.MAX, 'min': _lib.MIN,
+        'logsumexp': _lib.LOGSUMEXP}
+
+
+def require_cuda(*tensors: Tensor) -> torch.device:
+    dev = None
+    for t in tensors:
+        if t is None:
+            continue
+        if not t.is_cuda:
+            raise RuntimeError(
+                'torchrua_b200 runs on CUDA tensors only (hand-written sm_100a kernels, no CPU fallback); '
+                f'got a tensor on {t.device}')
+        if dev is None:
+            dev = t.device
+        elif t.device != dev:
+            raise RuntimeError(f'torchrua_b200: tensors on different devices ({dev} vs {t.device})')
+    return dev
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _ptr(t: Optional[Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+def _i64(t: Tensor) -> Tensor:
+    t = t.detach()
+    if t.dtype != torch.long:
+        t = t.long()
+    return t.contiguous()
+
+
+def scalar_bytes(value, dtype: torch.dtype) -> bytes:
+    """the in-memory image of ``value`` cast to ``dtype`` (fill / zero / one patterns)."""
+    t = torch.tensor([value], dtype=dtype)
+    return bytes(t.view(torch.uint8).tolist())
+
+
+# ------------------------------------------------------------------------------------------------
+# K0: metadata
+# ------------------------------------------------------------------------------------------------
+INT64_MAX = (1 << 63) - 1
+
+
+def scan(sizes: Tensor, clamp_max: int = INT64_MAX) -> Tuple[Tensor, Tensor]:
+    """(off[n+1], stats[2] = (sum, max)) of an int64 device vector; no host sync."""
+    lib = _lib.load()
+    sizes = _i64(sizes)
+    require_cuda(sizes)
+    n = sizes.numel()
+    with torch.cuda.device(sizes.device):
+        off = torch.empty(n + 1, dtype=torch.long, device=sizes.device)
+        stats = torch.empty(2, dtype=torch.long, device=sizes.device)
+        nbytes = lib.rua_scan_workspace_bytes(n)
+        ws = torch.empty(nbytes, dtype=torch.uint8, device=sizes.device)
+        _lib.check(lib.rua_scan_lengths(sizes.data_ptr(), n, clamp_max, off.data_ptr(), stats.data_ptr(),
+                                        ws.data_ptr(), nbytes, _stream()), 'rua_scan_lengths')
+    return off, stats
+
+
+@dataclass
+class Ragged:
+    """device-side description of a ragged batch (base lengths) shared by every kernel call."""
+    device: torch.device
+    B: int
+    len: Tensor                      # (B,) int64
+    off: Tensor                      # (B+1,) int64
+    stats: Optional[Tensor] = None   # (2,) int64 on device: (N, T)
+    _N: Optional[int] = None
+    _T: Optional[int] = None
+    # pack side
+    sorted: Optional[Tensor] = None
+    unsorted: Optional[Tensor] = None
+    bs_dev: Optional[Tensor] = None   # (Tp,)
+    poff: Optional[Tensor] = None     # (Tp+1,)
+    bs_cpu: Optional[Tensor] = None
+    Tp: int = 0
+    _keep: list = field(default_factory=list)
+
+    def _sync_stats(self):
+        n, t = self.stats.tolist()   # the one inherent D2H: output shapes depend on device data
+        self._N, self._T = int(n), int(t)
+
+    @property
+    def N(self) -> int:
+        if self._N is None:
+            self._sync_stats()
+        return self._N
+
+    @property
+    def T(self) -> int:
+        if self._T is None:
+            self._sync_stats()
+        return self._T
+
+    def c_struct(self) -> _lib.Ragged:
+        return _lib.Ragged(self.B, _ptr(self.off), _ptr(self.poff), _ptr(self.sorted), _ptr(self.unsorted), self.Tp)
+
+    def ensure_pack(self) -> 'Ragged':
+        """add (sorted, unsorted, batch_sizes, poff) for a lengths-based batch: device radix sort (stable
+        descending) + one binary search per time step; batch_sizes goes to the host because
+        PackedSequence requires it there (torchrua/core/view.py:55)."""
+        if self.sorted is not None and self.poff is not None:
+            return self
+        lib = _lib.load()
+        dev = self.device
+        T = self.T
+        with torch.cuda.device(dev):
+            if self.sorted is None:
+                self.sorted = torch.empty(self.B, dtype=torch.long, device=dev)
+                self.unsorted = torch.empty(self.B, dtype=torch.long, device=dev)
+                nbytes = lib.rua_sort_workspace_bytes(self.B)
+                ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+                _lib.check(lib.rua_sort_lengths(self.len.data_ptr(), self.B, T, self.sorted.data_ptr(),
+                                                self.unsorted.data_ptr(), ws.data_ptr(), nbytes, _stream()),
+                           'rua_sort_lengths')
+            self.bs_dev = torch.empty(T, dtype=torch.long, device=dev)
+            _lib.check(lib.rua_batch_sizes(self.len.data_ptr(), self.sorted.data_ptr(), self.B, T,
+                                           self.bs_dev.data_ptr(), _stream()), 'rua_batch_sizes')
+        self.poff, _ = scan(self.bs_dev)
+        self.Tp = T
+        self.bs_cpu = self.bs_dev.cpu()
+        return self
+
+
+_CACHE = {}
+_CACHE_LIMIT = 64
+
+
+def _cache_get(key_tensor: Tensor, tag: str):
+    ent = _CACHE.get((id(key_tensor), tag))
+    if ent is None:
+        return None
+    ref, version, value = ent
+    if ref() is key_tensor and key_tensor._version == version:
+        return value
+    del _CACHE[(id(key_tensor), tag)]
+    return None
+
+
+def _cache_put(key_tensor: Tensor, tag: str, value):
+    if len(_CACHE) >= _CACHE_LIMIT:
+        _CACHE.pop(next(iter(_CACHE)))
+    _CACHE[(id(key_tensor), tag)] = (weakref.ref(key_tensor), key_tensor._version, value)
+
+
+def ragged_from_lengths(token_sizes: Tensor) -> Ragged:
+    """lengths -> Ragged (one scan kernel; cached per lengths tensor object + version)."""
+    hit = _cache_get(token_sizes, 'len')
+    if hit is not None:
+        return hit
+    dev = require_cuda(token_sizes)
+    lens = _i64(token_sizes)
+    off, stats = scan(lens)
+    rg = Ragged(device=dev, B=lens.numel(), len=lens, off=off, stats=stats)
+    _cache_put(token_sizes, 'len', rg)
+    return rg
+
+
+def ragged_from_pack(batch_sizes: Tensor, sorted_indices: Optional[Tensor], unsorted_indices: Optional[Tensor],
+                     device: torch.device, n_rows: int) -> Ragged:
+    """PackedSequence metadata -> Ragged.  No device->host sync: B, T and N are known on the host
+    (batch_sizes lives there by PyTorch's contract)."""
+    key = unsorted_indices if unsorted_indices is not None else batch_sizes
+    hit = _cache_get(key, 'pack')
+    if hit is not None and hit.bs_cpu is batch_sizes:
+        return hit
+    lib = _lib.load()
+    bs_cpu = batch_sizes.detach()
+    if bs_cpu.is_cuda:
+        bs_cpu = bs_cpu.cpu()
+    bs_cpu = bs_cpu.long().contiguous()
+    Tp = bs_cpu.numel()
+    # B counts every sequence, including empty ones that never show up in batch_sizes
+    B = unsorted_indices.numel() if unsorted_indices is not None else (int(bs_cpu[0]) if Tp > 0 else 0)
+    with torch.cuda.device(device):
+        # one H2D for [batch_sizes | poff]
+        host = torch.empty(2 * Tp + 1, dtype=torch.long)
+        host[:Tp] = bs_cpu
+        host[Tp] = 0
+        torch.cumsum(bs_cpu, dim=0, out=host[Tp + 1:])
+        devbuf = host.to(device, non_blocking=False)
+        bs_dev, poff = devbuf[:Tp], devbuf[Tp:]
+        if unsorted_indices is None:   # enforce_sorted=True packs carry no permutation: identity
+            unsorted = torch.arange(B, dtype=torch.long, device=device)
+            srt = unsorted
+        else:
+            unsorted = _i64(unsorted_indices)
+            srt = _i64(sorted_indices)
+        require_cuda(unsorted, srt)
+        lens = torch.empty(B, dtype=torch.long, device=device)
+        _lib.check(lib.rua_lengths_from_pack(bs_dev.data_ptr() if Tp else None, unsorted.data_ptr(), B, Tp,
+                                             lens.data_ptr(), _stream()), 'rua_lengths_from_pack')
+    off, stats = scan(lens)
+    rg = Ragged(device=device, B=B, len=lens, off=off, stats=stats, _N=int(host[-1]) if Tp else 0, _T=Tp,
+                sorted=srt, unsorted=unsorted, bs_dev=bs_dev, poff=poff, bs_cpu=batch_sizes, Tp=Tp)
+    rg._keep.append(devbuf)
+    _cache_put(key, 'pack', rg)
+    return rg
+
+
+def with_injected_pack(rg: Ragged, sorted_indices: Tensor) -> Ragged:
+    """a copy of ``rg`` whose pack side uses an externally supplied permutation (parity mode: feed the
+    reference's non-stable sorted_indices and get bit-identical P data, SURVEY.md 8c hazard 1)."""
+    lib = _lib.load()
+    srt = _i64(sorted_indices)
+    require_cuda(srt)
+    new = Ragged(device=rg.device, B=rg.B, len=rg.len, off=rg.off, stats=rg.stats, _N=rg._N, _T=rg._T)
+    new.sorted = srt
+    new.unsorted = torch.empty_like(srt)
+    with torch.cuda.device(rg.device):
+        _lib.check(lib.rua_invert_permutation(srt.data_ptr(), rg.B, new.unsorted.data_ptr(), _stream()),
+                   'rua_invert_permutation')
+    return new.ensure_pack()
+
+
+def invert_permutation(perm: Tensor) -> Tensor:
+    lib = _lib.load()
+    require_cuda(perm)
+    p = _i64(perm)
+    out = torch.empty_like(p)
+    with torch.cuda.device(p.device):
+        _lib.check(lib.rua_invert_permutation(p.data_ptr(), p.numel(), out.data_ptr(), _stream()),
+                   'rua_invert_permutation')
+    return out
+
+
+# ------------------------------------------------------------------------------------------------
+# K1/K2: ragged row map (+ autograd)
+# ------------------------------------------------------------------------------------------------
+@dataclass(frozen=True)
+class SideSpec:
+    layout: int
+    xform: int = LEN_SAME
+    arg: int = 0
+    width: int = 0
+    rows: int = 0
+
+    def c_struct(self) -> _lib.Side:
+        return _lib.Side(self.layout, self.xform, self.arg, self.width, self.rows)
+
+
+@dataclass(frozen=True)
+class MapSpec:
+    rg: Ragged
+    src: SideSpec
+    dst: SideSpec
+    tmap: int = MAP_SHIFT
+    tmap_arg: int = 0
+    pad_mode: int = PAD_FILL
+
+    def inverse(self) -> 'MapSpec':
+        """the map that routes gradients back: sides swapped, token map inverted, zero padding."""
+        arg = -self.tmap_arg if self.tmap in (MAP_SHIFT, MAP_ROLL) else 0
+        return MapSpec(self.rg, self.dst, self.src, self.tmap, arg, PAD_FILL)
+
+
+def _row_map_raw(src: Tensor, spec: MapSpec, fill: bytes, feat: Tuple[int, ...], dtype, device) -> Tensor:
+    lib = _lib.load()
+    rows = spec.dst.rows
+    out = torch.empty((rows,) + tuple(feat), dtype=dtype, device=device)
+    if rows == 0 or out.numel() == 0:
+        return out
+    row_bytes = out.element_size()
+    for f in feat:
+        row_bytes *= f
+    rg = spec.rg.c_struct()
+    s, d = spec.src.c_struct(), spec.dst.c_struct()
+    with torch.cuda.device(device):
+        _lib.check(lib.rua_row_map(_ptr(src), out.data_ptr(), row_bytes, ctypes.byref(rg), ctypes.byref(s),
+                                   ctypes.byref(d), spec.tmap, spec.tmap_arg, spec.pad_mode, fill, len(fill),
+                                   _stream()), 'rua_row_map')
+    return out
+
+
+class _RowMap(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, src: Tensor, spec: MapSpec, fill: bytes):
+        ctx.spec = spec
+        ctx.src_rows = src.shape[0]
+        flat = src.detach()
+        if not flat.is_contiguous():
+            flat = flat.contiguous()
+        return _row_map_raw(flat, spec, fill, tuple(src.shape[1:]), src.dtype, src.device)
+
+    @staticmethod
+    def backward(ctx, grad_out: Tensor):
+        spec: MapSpec = ctx.spec
+        inv = spec.inverse()
+        g = grad_out.contiguous()
+        zero = bytes(g.element_size())
+        grad_src = _row_map_raw(g, inv, zero, tuple(g.shape[1:]), g.dtype, g.device)
+        if spec.pad_mode == PAD_ROW0 and grad_src.shape[0] > 0:
+            # forward copied flat row 0 into every padding slot (L/R.roll quirk): those slots' gradients
+            # flow back into row 0.  Padding slots are exactly the rows the inverse map does not reach.
+            probe = MapSpec(spec.rg, spec.src, spec.dst, spec.tmap, spec.tmap_arg, PAD_FILL)
+            ones = torch.ones((ctx.src_rows, 1), dtype=torch.uint8, device=g.device)
+            hit = _row_map_raw(ones, probe, bytes(1), (1,), torch.uint8, g.device).view(-1).bool()
+            grad_src[0] += g[~hit].sum(dim=0)
+        return grad_src, None, None
+
+
+def row_map(src_flat: Tensor, spec: MapSpec, fill_value=0) -> Tensor:
+    """src_flat: (rows_src, *feat) contiguous flattened storage of the source layout."""
+    require_cuda(src_flat)
+    fill = scalar_bytes(fill_value, src_flat.dtype)
+    return _RowMap.apply(src_flat, spec, fill)
+
+
+class _GatherRows(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, src: Tensor, index: Tensor):
+        lib = _lib.load()
+        idx = _i64(index)
+        ctx.save_for_backward(idx)
+        ctx.src_shape = src.shape
+        flat = src.detach().contiguous()
+        out = torch.empty((idx.numel(),) + tuple(flat.shape[1:]), dtype=flat.dtype, device=flat.device)
+        if out.numel() > 0:
+            row_bytes = flat.element_size() * (flat[0].numel() if flat.shape[0] else 0)
+            with torch.cuda.device(flat.device):
+                _lib.check(lib.rua_gather_rows(flat.data_ptr(), flat.shape[0], idx.data_ptr(), idx.numel(),
+                                               row_bytes, out.data_ptr(), _stream()), 'rua_gather_rows')
+        return out.view(tuple(index.shape) + tuple(flat.shape[1:]))
+
+    @staticmethod
+    def backward(ctx, grad_out: Tensor):
+        (idx,) = ctx.saved_tensors
+        # arbitrary user indices may repeat: accumulate (deterministic sort-based ATen path; not on the
+        # hot path -- casts and selects never come through here)
+        grad = torch.zeros(ctx.src_shape, dtype=grad_out.dtype, device=grad_out.device)
+        grad.index_put_((idx.view(-1),), grad_out.reshape((-1,) + tuple(ctx.src_shape[1:])), accumulate=True)
+        return grad, None
+
+
+def gather_rows(src: Tensor, index: Tensor) -> Tensor:
+    require_cuda(src, index)
+    return _GatherRows.apply(src, index)
+
+
+def scatter_rows_(dst: Tensor, index: Tensor, value: Tensor) -> None:
+    """dst[index[j]] = value[j] in place (no autograd; mirrors Tensor.__setitem__ on .data)."""
+    lib = _lib.load()
+    require_cuda(dst, index)
+    if not dst.is_contiguous():
+        raise RuntimeError('torchrua_b200: in-place scatter needs a contiguous destination')
+    idx = _i64(index).view(-1)
+    feat = tuple(dst.shape[1:])
+    val = torch.as_tensor(value, dtype=dst.dtype, device=dst.device)
+    val = val.expand((idx.numel(),) + feat).contiguous()
+    if val.numel() == 0:
+        return
+    row_bytes = dst.element_size() * (dst[0].numel())
+    with torch.cuda.device(dst.device):
+        _lib.check(lib.rua_scatter_rows(val.data_ptr(), idx.data_ptr(), idx.numel(), row_bytes, dst.data_ptr(),
+                                        dst.shape[0], _stream()), 'rua_scatter_rows')
+
+
+# ------------------------------------------------------------------------------------------------
+# K3: mask / index emit
+# ------------------------------------------------------------------------------------------------
+def mask(rg: Ragged, width: int, zero, one, dtype: torch.dtype) -> Tensor:
+    lib = _lib.load()
+    out = torch.empty((rg.B, width), dtype=dtype, device=rg.device)
+    if out.numel() == 0:
+        return out
+    z, o = scalar_bytes(zero, dtype), scalar_bytes(one, dtype)
+    with torch.cuda.device(rg.device):
+        _lib.check(lib.rua_mask(rg.len.data_ptr(), rg.B, width, z, o, out.element_size(), out.data_ptr(),
+                                _stream()), 'rua_mask')
+    return out
+
+
+def emit_ptr(off: Tensor, n: int, relabel: Optional[Tensor] = None, want_which=True, want_within=True,
+             flat_stride: int = 0, right_align: bool = False):
+    lib = _lib.load()
+    dev = off.device
+    S = off.numel() - 1
+    which = torch.empty(n, dtype=torch.long, device=dev) if want_which else None
+    within = torch.empty(n, dtype=torch.long, device=dev) if want_within else None
+    flat = torch.empty(n, dtype=torch.long, device=dev) if flat_stride else None
+    if n > 0:
+        with torch.cuda.device(dev):
+            _lib.check(lib.rua_emit_ptr(off.data_ptr(), S, n, _ptr(relabel), _ptr(which), _ptr(within), _ptr(flat),
+                                        flat_stride, int(right_align), _stream()), 'rua_emit_ptr')
+    return which, within, flat
+
+
+# ------------------------------------------------------------------------------------------------
+# K4: segment reduce (+ autograd)
+# ------------------------------------------------------------------------------------------------
+def _reduce_raw(data: Tensor, off: Tensor, S: int, op: int) -> Tensor:
+    lib = _lib.load()
+    if data.dtype not in _DTYPES:
+        raise RuntimeError(f'torchrua_b200: segment reductions support float16/bfloat16/float32/float64, got '
+                           f'{data.dtype} (the reference rejects integer data too: "_segment_reduce" not '
+                           f'implemented for Long)')
+    N = data.shape[0]
+    feat = tuple(data.shape[1:])
+    H = 1
+    for f in feat:
+        H *= f
+    out = torch.empty((S,) + feat, dtype=data.dtype, device=data.device)
+    if out.numel() == 0:
+        return out
+    dt = _DTYPES[data.dtype]
+    with torch.cuda.device(data.device):
+        nbytes = lib.rua_segment_reduce_workspace_bytes(N, S, H, dt, op)
+        ws = torch.empty(nbytes, dtype=torch.uint8, device=data.device)
+        _lib.check(lib.rua_segment_reduce(_ptr(data), off.data_ptr(), N, S, H, dt, op, out.data_ptr(), ws.data_ptr(),
+                                          nbytes, _stream()), 'rua_segment_reduce')
+    return out
+
+
+class _SegmentReduce(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, data: Tensor, off: Tensor, S: int, op: int):
+        flat = data.detach()
+        if not flat.is_contiguous():
+            flat = flat.contiguous()
+        out = _reduce_raw(flat, off, S, op)
+        ctx.op = op
+        ctx.S = S
+        ctx.save_for_backward(flat, off, out)
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_out: Tensor):
+        lib = _lib.load()
+        data, off, out = ctx.saved_tensors
+        g = grad_out.contiguous()
+        N = data.shape[0]
+        H = data[0].numel() if N else 0
+        grad = torch.empty_like(data)
+        if grad.numel() > 0:
+            dt = _DTYPES[data.dtype]
+            with torch.cuda.device(data.device):
+                nbytes = lib.rua_segment_reduce_backward_workspace_bytes(N, ctx.S, H, dt, ctx.op)
+                ws = torch.empty(max(nbytes, 16), dtype=torch.uint8, device=data.device)
+                _lib.check(lib.rua_segment_reduce_backward(g.data_ptr(), out.data_ptr(), data.data_ptr(),
+                                                           off.data_ptr(), N, ctx.S, H, dt, ctx.op, grad.data_ptr(),
+                                                           ws.data_ptr(), nbytes, _stream()),
+                           'rua_segment_reduce_backward')
+        return grad, None, None, None
+
+
+def segment_reduce(data: Tensor, segment_sizes: Tensor, op: str) -> Tensor:
+    require_cuda(data, segment_sizes)
+    rg = ragged_from_lengths(segment_sizes)
+    return _SegmentReduce.apply(data, rg.off, rg.B, _OPS[op])

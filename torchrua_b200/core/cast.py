@@ -1,0 +1,94 @@
+"""The 12 directed layout conversions -- mirror of torchrua/core/cast.py, every one a single launch of
+the ragged row-map kernel (rua_row_map) with the padding fill fused in.
+
+reference: to_cat cast.py:8-16, cat_pack_to_left :19-23, right_to_left :26-32, to_pack :41-49,
+cat_pack_to_right :52-56, left_to_right :59-65.
+"""
+from numbers import Number
+from typing import Optional
+
+from torch import Tensor
+
+from torchrua_b200 import _native
+from torchrua_b200._lib import CAT, LEFT, PACK, RIGHT
+from torchrua_b200._native import MapSpec, SideSpec
+from torchrua_b200.layout import C, L, P, R, Z
+from torchrua_b200.utils import to_self
+
+
+def side_of(self: Z, rg: '_native.Ragged') -> SideSpec:
+    """describe the storage of ``self`` to the kernel."""
+    if isinstance(self, C):
+        return SideSpec(CAT, rows=self.data.size()[0])
+    if isinstance(self, P):
+        return SideSpec(PACK, rows=self.data.size()[0])
+    b, w = self.data.size()[:2]
+    return SideSpec(RIGHT if isinstance(self, R) else LEFT, width=w, rows=b * w)
+
+
+def _convert(self: Z, rg: '_native.Ragged', dst: SideSpec, fill_value: Number = 0) -> Tensor:
+    spec = MapSpec(rg=rg, src=side_of(self, rg), dst=dst)
+    return _native.row_map(self.raw(), spec, fill_value)
+
+
+def to_cat(self: Z) -> C:
+    rg = self._ragged()
+    data = _convert(self, rg, SideSpec(CAT, rows=rg.N))
+    return C(data=data, token_sizes=self.token_sizes if not isinstance(self, P) else rg.len)
+
+
+C.cat = to_self
+L.cat = to_cat
+R.cat = to_cat
+P.cat = to_cat
+
+
+def _to_padded(self: Z, layout: int, fill_value: Number):
+    rg = self._ragged()
+    b, t = rg.B, rg.T
+    data = _convert(self, rg, SideSpec(layout, width=t, rows=b * t), fill_value)
+    data = data.view((b, t) + tuple(data.size()[1:]))
+    return data, (self.token_sizes if not isinstance(self, P) else rg.len)
+
+
+def to_left(self: Z, fill_value: Number = 0) -> L:
+    data, token_sizes = _to_padded(self, LEFT, fill_value)
+    return L(data=data, token_sizes=token_sizes)
+
+
+cat_pack_to_left = to_left
+right_to_left = to_left
+
+C.left = to_left
+L.left = to_self
+P.left = to_left
+R.left = to_left
+
+
+def to_pack(self: Z, sorted_indices: Optional[Tensor] = None) -> P:
+    """``sorted_indices`` (extension): pack with an externally supplied permutation instead of the
+    device sort -- parity mode against the reference's non-stable CPU sort (SURVEY.md 8c hazard 1)."""
+    rg = self._ragged()
+    rg = rg.ensure_pack() if sorted_indices is None else _native.with_injected_pack(rg, sorted_indices)
+    data = _convert(self, rg, SideSpec(PACK, rows=rg.N))
+    return P(data=data, batch_sizes=rg.bs_cpu, sorted_indices=rg.sorted, unsorted_indices=rg.unsorted)
+
+
+C.pack = to_pack
+L.pack = to_pack
+P.pack = to_self
+R.pack = to_pack
+
+
+def to_right(self: Z, fill_value: Number = 0) -> R:
+    data, token_sizes = _to_padded(self, RIGHT, fill_value)
+    return R(data=data, token_sizes=token_sizes)
+
+
+cat_pack_to_right = to_right
+left_to_right = to_right
+
+C.right = to_right
+L.right = to_right
+P.right = to_right
+R.right = to_self

@@ -1,0 +1,403 @@
+// K4 -- segment reduce (forward): sum / mean / prod / max / min / logsumexp per contiguous segment.
+//
+// Replaces (reference file:line): segment_max torchrua/reduce.py:34-36, segment_min :39-41,
+// segment_sum :44-45, segment_mean :48-49, segment_prod :52-53, segment_logsumexp :56-61.
+// The reference calls ATen segment_reduce (one thread per output, serial walk over the segment,
+// accumulation in the storage dtype) and, for logsumexp, ~5 extra passes and 3 N x H temporaries.
+//
+// Design (HBM-bound: N*D bytes read once, S*D written once):
+//   * the N rows are cut into fixed chunks of R rows, whatever the segment lengths -- a Zipf batch
+//     (38 % of segments of length 1, 1 % of length 4096) is balanced by construction;
+//   * a CTA owns (chunk, 128 column-vectors); a thread owns one 16-byte column vector and walks the
+//     chunk's rows top to bottom, 8 independent 128-bit loads in flight, fp32 (fp64) accumulators
+//     in registers; lanes map to columns, so every load/store is fully coalesced along H;
+//   * segment boundaries are uniform across the CTA (all threads see the same rows): a segment
+//     that starts and ends inside the chunk is finalised and stored directly; the pieces of a
+//     segment that crosses chunk boundaries go to a small fp32 scratch (at most 2 rows per chunk)
+//     and are combined IN CHUNK ORDER by a second tiny kernel -- deterministic, no float atomics;
+//   * logsumexp is one pass (online max / rescaled sum, one exp per element);
+//   * the reference's `initial` quirks (SURVEY.md 8c hazard 3) cost no extra pass: the global
+//     extreme is reduced on the fly (one atomic per CTA) and a NaN is detected at emit time; a
+//     third tiny kernel patches empty segments and applies the NaN poisoning.
+#include "reduce_common.cuh"
+
+namespace rua {
+
+struct RedHeader {            // first 64 bytes of the workspace
+  unsigned long long ext_key; // global min (max / logsumexp) or global max (min), as an order key
+  unsigned int nan_flag;      // a NaN reached an output of max / min / logsumexp
+  unsigned int pad[13];
+};
+
+template <int OP> struct OpInfo {
+  static constexpr bool kIsLse = OP == RUA_LOGSUMEXP;
+  static constexpr bool kNeedsExt = OP == RUA_MAX || OP == RUA_MIN || OP == RUA_LOGSUMEXP;
+  static constexpr int kParts = kIsLse ? 2 : 1;  // accumulator planes (lse keeps max and sum)
+};
+
+// accumulator state for V columns
+template <typename A, int V, int OP>
+struct State {
+  A a[V];   // sum / prod / max / min, or the running max for logsumexp
+  A s[OpInfo<OP>::kIsLse ? V : 1];
+
+  __device__ __forceinline__ void reset() {
+#pragma unroll
+    for (int v = 0; v < V; ++v) {
+      if (OP == RUA_SUM || OP == RUA_MEAN) a[v] = A(0);
+      else if (OP == RUA_PROD) a[v] = A(1);
+      else if (OP == RUA_MIN) a[v] = inf_of<A>();
+      else a[v] = -inf_of<A>();
+      if (OpInfo<OP>::kIsLse) s[v] = A(0);
+    }
+  }
+  template <bool kFast>
+  __device__ __forceinline__ void add(const A* x) {
+#pragma unroll
+    for (int v = 0; v < V; ++v) {
+      if (OP == RUA_SUM || OP == RUA_MEAN) a[v] += x[v];
+      else if (OP == RUA_PROD) a[v] *= x[v];
+      else if (OP == RUA_MAX) a[v] = max_nan(a[v], x[v]);
+      else if (OP == RUA_MIN) a[v] = min_nan(a[v], x[v]);
+      else {  // online logsumexp: one exp per element
+        A d = x[v] - a[v];
+        A e = exp_acc<kFast>(-abs_acc(d));
+        s[v] = d > A(0) ? s[v] * e + A(1) : s[v] + e;
+        a[v] = max_nan(a[v], x[v]);
+      }
+    }
+  }
+  // merge a later piece (b) into this earlier piece, in order
+  template <bool kFast>
+  __device__ __forceinline__ void merge(const State& b) {
+#pragma unroll
+    for (int v = 0; v < V; ++v) {
+      if (OP == RUA_SUM || OP == RUA_MEAN) a[v] += b.a[v];
+      else if (OP == RUA_PROD) a[v] *= b.a[v];
+      else if (OP == RUA_MAX) a[v] = max_nan(a[v], b.a[v]);
+      else if (OP == RUA_MIN) a[v] = min_nan(a[v], b.a[v]);
+      else {
+        A m = max_nan(a[v], b.a[v]);
+        A s1 = s[v] == A(0) ? A(0) : s[v] * exp_acc<kFast>(a[v] - m);
+        A s2 = b.s[v] == A(0) ? A(0) : b.s[v] * exp_acc<kFast>(b.a[v] - m);
+        s[v] = s1 + s2;
+        a[v] = m;
+      }
+    }
+  }
+  __device__ __forceinline__ void finalize(int64_t len, A* out) const {
+#pragma unroll
+    for (int v = 0; v < V; ++v) {
+      if (OP == RUA_MEAN) out[v] = (a[v] != a[v]) ? a[v] : a[v] / (A)len;
+      else if (OP == RUA_LOGSUMEXP) out[v] = log_acc(s[v]) + a[v];
+      else out[v] = a[v];
+    }
+  }
+  __device__ __forceinline__ bool any_nan_out(const A* out) const {
+    bool n = false;
+#pragma unroll
+    for (int v = 0; v < V; ++v) n |= (out[v] != out[v]);
+    return n;
+  }
+};
+
+template <typename A, int V, int OP>
+__device__ __forceinline__ void store_partial(A* base, int64_t H, int64_t col, const State<A, V, OP>& st) {
+#pragma unroll
+  for (int v = 0; v < V; ++v) {
+    base[col + v] = st.a[v];
+    if (OpInfo<OP>::kIsLse) base[H + col + v] = st.s[v];
+  }
+}
+template <typename A, int V, int OP>
+__device__ __forceinline__ void load_partial(const A* base, int64_t H, int64_t col, State<A, V, OP>& st) {
+#pragma unroll
+  for (int v = 0; v < V; ++v) {
+    st.a[v] = base[col + v];
+    if (OpInfo<OP>::kIsLse) st.s[v] = base[H + col + v];
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// main kernel
+// ---------------------------------------------------------------------------------------------
+template <typename T, int V, int OP>
+__global__ void __launch_bounds__(kRedThreads)
+segreduce_kernel(const T* __restrict__ data, const int64_t* __restrict__ off, int64_t N, int64_t S, int64_t H,
+                 int R, T* __restrict__ out, typename Store<T>::Acc* __restrict__ head,
+                 typename Store<T>::Acc* __restrict__ tail, RedHeader* hdr) {
+  using A = typename Store<T>::Acc;
+  constexpr bool kFast = sizeof(T) == 2;  // 16-bit storage: 1e-2 tolerance, approximate exp is plenty
+  constexpr int P = OpInfo<OP>::kParts;
+  const int64_t chunk = blockIdx.x;
+  const int64_t col = ((int64_t)blockIdx.y * blockDim.x + threadIdx.x) * V;
+  const bool active = col < H;
+  const int64_t row0 = chunk * R;
+  const int64_t row1 = row0 + R < N ? row0 + R : N;
+
+  GlobalOff g{off};
+  int64_t s = owner_search(g, S, row0);
+  int64_t seg_beg = __ldg(off + s), seg_end = __ldg(off + s + 1);
+  bool open = seg_beg < row0;   // the segment began in an earlier chunk
+  bool pending = false;
+
+  State<A, V, OP> st;
+  st.reset();
+  A ext = OP == RUA_MIN ? -inf_of<A>() : inf_of<A>();
+  bool saw_nan = false;
+
+  const T* colp = data + col;
+  for (int64_t r = row0; r < row1; r += kRedUnroll) {
+    Raw<T, V> raw[kRedUnroll];
+    if (active) {
+#pragma unroll
+      for (int k = 0; k < kRedUnroll; ++k)
+        if (r + k < row1) load_raw<T, V>(colp + (r + k) * H, raw[k]);
+    }
+#pragma unroll
+    for (int k = 0; k < kRedUnroll; ++k) {
+      const int64_t row = r + k;
+      if (row < row1) {
+        if (active) {
+          A x[V];
+          unpack_raw<T, V>(raw[k], x);
+          st.template add<kFast>(x);
+          if (OpInfo<OP>::kNeedsExt) {
+#pragma unroll
+            for (int v = 0; v < V; ++v) ext = OP == RUA_MIN ? max_num(ext, x[v]) : min_num(ext, x[v]);
+          }
+        }
+        pending = true;
+        if (row + 1 == seg_end) {  // uniform across the CTA
+          if (active) {
+            if (open) {
+              store_partial<A, V, OP>(head + chunk * P * H, H, col, st);
+            } else {
+              A o[V];
+              st.finalize(seg_end - seg_beg, o);
+              if (OpInfo<OP>::kNeedsExt) saw_nan |= st.any_nan_out(o);
+              store_vec<T, V>(out + s * H + col, o);
+            }
+          }
+          st.reset();
+          open = false;
+          pending = false;
+          do {  // next non-empty segment
+            ++s;
+            seg_beg = seg_end;
+            seg_end = s < S ? __ldg(off + s + 1) : (int64_t)0x7fffffffffffffffll;
+          } while (s < S && seg_end == seg_beg);
+        }
+      }
+    }
+  }
+  if (pending && active) {
+    // the segment continues in the next chunk: whole-chunk pieces go to `head`, suffix pieces to `tail`
+    store_partial<A, V, OP>((open ? head : tail) + chunk * P * H, H, col, st);
+    if (OpInfo<OP>::kNeedsExt) {
+#pragma unroll
+      for (int v = 0; v < V; ++v) saw_nan |= (st.a[v] != st.a[v]);
+    }
+  }
+
+  if (OpInfo<OP>::kNeedsExt) {
+    __shared__ unsigned long long s_key[kRedThreads / 32];
+    __shared__ int s_nan;
+    if (threadIdx.x == 0) s_nan = 0;
+    __syncthreads();
+    unsigned long long key = order_key(ext);
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) {
+      unsigned long long o = __shfl_xor_sync(kFullMask, key, d);
+      key = OP == RUA_MIN ? (o > key ? o : key) : (o < key ? o : key);
+    }
+    if ((threadIdx.x & 31) == 0) s_key[threadIdx.x >> 5] = key;
+    if (saw_nan) s_nan = 1;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      for (int w = 1; w < (int)(blockDim.x >> 5); ++w) {
+        unsigned long long o = s_key[w];
+        key = OP == RUA_MIN ? (o > key ? o : key) : (o < key ? o : key);
+      }
+      if (OP == RUA_MIN) atomicMax(&hdr->ext_key, key); else atomicMin(&hdr->ext_key, key);
+      if (s_nan) atomicOr(&hdr->nan_flag, 1u);
+    }
+  }
+}
+
+// combine the pieces of every segment that crosses a chunk boundary, in chunk order
+template <typename T, int V, int OP>
+__global__ void __launch_bounds__(kRedThreads)
+segreduce_span_kernel(const int64_t* __restrict__ off, int64_t N, int64_t S, int64_t H, int R,
+                      T* __restrict__ out, const typename Store<T>::Acc* __restrict__ head,
+                      const typename Store<T>::Acc* __restrict__ tail, RedHeader* hdr) {
+  using A = typename Store<T>::Acc;
+  constexpr bool kFast = sizeof(T) == 2;
+  constexpr int P = OpInfo<OP>::kParts;
+  const int64_t b = blockIdx.x;            // boundary between chunk b and b+1
+  const int64_t jb = (b + 1) * R;
+  if (jb >= N) return;
+  GlobalOff g{off};
+  const int64_t s = owner_search(g, S, jb);
+  const int64_t beg = __ldg(off + s), end = __ldg(off + s + 1);
+  if (beg >= jb) return;        // a segment starts exactly here: nothing crosses
+  if (beg < b * R) return;      // it began before chunk b: an earlier boundary owns it
+  const int64_t col = ((int64_t)blockIdx.y * blockDim.x + threadIdx.x) * V;
+  if (col >= H) return;
+  State<A, V, OP> acc, piece;
+  load_partial<A, V, OP>(tail + b * P * H, H, col, acc);
+  for (int64_t c = b + 1;; ++c) {
+    load_partial<A, V, OP>(head + c * P * H, H, col, piece);
+    acc.template merge<kFast>(piece);
+    if (end <= (c + 1) * R) break;
+  }
+  A o[V];
+  acc.finalize(end - beg, o);
+  if (OpInfo<OP>::kNeedsExt && acc.any_nan_out(o)) atomicOr(&hdr->nan_flag, 1u);
+  store_vec<T, V>(out + s * H + col, o);
+}
+
+// empty segments and NaN poisoning (reference `initial` semantics, reduce.py:35,40,57-61)
+template <typename T, int V, int OP>
+__global__ void __launch_bounds__(256)
+segreduce_patch_kernel(const int64_t* __restrict__ off, int64_t S, int64_t H, T* __restrict__ out,
+                       const RedHeader* __restrict__ hdr) {
+  using A = typename Store<T>::Acc;
+  const int64_t hv = H / V;
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= S * hv) return;
+  const int64_t s = idx / hv;
+  const int64_t col = (idx - s * hv) * V;
+  const bool poison = OpInfo<OP>::kNeedsExt && hdr->nan_flag != 0;
+  const bool empty = __ldg(off + s + 1) == __ldg(off + s);
+  if (!poison && !empty) return;
+  A val;
+  if (poison) val = nan_of<A>();
+  else if (OP == RUA_SUM || OP == RUA_MEAN) val = A(0);
+  else if (OP == RUA_PROD) val = A(1);
+  else val = key_to(A(0), hdr->ext_key);
+  A o[V];
+#pragma unroll
+  for (int v = 0; v < V; ++v) o[v] = val;
+  store_vec<T, V>(out + s * H + col, o);
+}
+
+__global__ void segreduce_init_kernel(RedHeader* hdr, int is_min) {
+  hdr->ext_key = is_min ? 0ull : ~0ull;
+  hdr->nan_flag = 0u;
+}
+
+struct RedPlan {
+  int R;
+  int64_t chunks;
+  int threads;
+  int64_t col_tiles;
+  int vec;
+  size_t part_elems;  // per partial array
+};
+
+static RedPlan plan_reduce(int64_t N, int64_t H, int32_t dtype, int32_t op, const void* data, const void* out) {
+  RedPlan p;
+  int full = dtype == RUA_F32 ? 4 : (dtype == RUA_F64 ? 2 : 8);
+  bool aligned = (H % full == 0) && (((uintptr_t)data | (uintptr_t)out) & 15u) == 0;
+  p.vec = aligned ? full : 1;
+  int64_t hv = H / p.vec;
+  int threads = 32;
+  while (threads < kRedThreads && threads < hv) threads <<= 1;
+  p.threads = threads;
+  p.col_tiles = ceil_div(hv, threads);
+  // largest chunk that still gives every SM ~8 CTAs
+  int R = 256;
+  while (R > 32 && ceil_div(N, R) * p.col_tiles < (int64_t)kNumSMs * 8) R >>= 1;
+  p.R = R;
+  p.chunks = N > 0 ? ceil_div(N, R) : 0;
+  p.part_elems = (size_t)p.chunks * (size_t)H * (op == RUA_LOGSUMEXP ? 2 : 1);
+  return p;
+}
+
+template <typename T, int V, int OP>
+static int run_reduce(const RedPlan& p, const void* data, const int64_t* off, int64_t N, int64_t S, int64_t H,
+                      void* out, void* ws, cudaStream_t st) {
+  using A = typename Store<T>::Acc;
+  RedHeader* hdr = (RedHeader*)ws;
+  A* head = (A*)((char*)ws + sizeof(RedHeader));
+  A* tail = head + p.part_elems;
+  int rc;
+  if (OpInfo<OP>::kNeedsExt) {
+    segreduce_init_kernel<<<1, 1, 0, st>>>(hdr, OP == RUA_MIN);
+    if ((rc = check_launch())) return rc;
+  }
+  if (N > 0) {
+    if (p.col_tiles > 65535) return RUA_ERR_UNSUPPORTED;
+    dim3 grid((unsigned)p.chunks, (unsigned)p.col_tiles);
+    segreduce_kernel<T, V, OP><<<grid, p.threads, 0, st>>>((const T*)data, off, N, S, H, p.R, (T*)out, head, tail, hdr);
+    if ((rc = check_launch())) return rc;
+    if (p.chunks > 1) {
+      dim3 g2((unsigned)(p.chunks - 1), (unsigned)p.col_tiles);
+      segreduce_span_kernel<T, V, OP><<<g2, p.threads, 0, st>>>(off, N, S, H, p.R, (T*)out, head, tail, hdr);
+      if ((rc = check_launch())) return rc;
+    }
+  }
+  int64_t total = S * (H / V);
+  segreduce_patch_kernel<T, V, OP><<<(unsigned)ceil_div(total, 256), 256, 0, st>>>(off, S, H, (T*)out, hdr);
+  return check_launch();
+}
+
+template <typename T, int V>
+static int dispatch_op(int32_t op, const RedPlan& p, const void* data, const int64_t* off, int64_t N, int64_t S,
+                       int64_t H, void* out, void* ws, cudaStream_t st) {
+  switch (op) {
+    case RUA_SUM: return run_reduce<T, V, RUA_SUM>(p, data, off, N, S, H, out, ws, st);
+    case RUA_MEAN: return run_reduce<T, V, RUA_MEAN>(p, data, off, N, S, H, out, ws, st);
+    case RUA_PROD: return run_reduce<T, V, RUA_PROD>(p, data, off, N, S, H, out, ws, st);
+    case RUA_MAX: return run_reduce<T, V, RUA_MAX>(p, data, off, N, S, H, out, ws, st);
+    case RUA_MIN: return run_reduce<T, V, RUA_MIN>(p, data, off, N, S, H, out, ws, st);
+    case RUA_LOGSUMEXP: return run_reduce<T, V, RUA_LOGSUMEXP>(p, data, off, N, S, H, out, ws, st);
+    default: return RUA_ERR_INVALID;
+  }
+}
+
+template <typename T>
+static int dispatch_vec(int32_t op, const RedPlan& p, const void* data, const int64_t* off, int64_t N, int64_t S,
+                        int64_t H, void* out, void* ws, cudaStream_t st) {
+  if (p.vec == 1) return dispatch_op<T, 1>(op, p, data, off, N, S, H, out, ws, st);
+  return dispatch_op<T, Store<T>::kVec>(op, p, data, off, N, S, H, out, ws, st);
+}
+
+}  // namespace rua
+
+using namespace rua;
+
+extern "C" {
+
+size_t rua_segment_reduce_workspace_bytes(int64_t N, int64_t S, int64_t H, int32_t dtype, int32_t op) {
+  (void)S;
+  RedPlan p = plan_reduce(N, H, dtype, op, nullptr, nullptr);
+  // the vector width may drop to 1 for misaligned views; that only changes threads/tiles, not R... be safe:
+  RedPlan q = plan_reduce(N, H, dtype, op, (const void*)1, nullptr);
+  size_t elems = p.part_elems > q.part_elems ? p.part_elems : q.part_elems;
+  size_t acc = dtype == RUA_F64 ? 8 : 4;
+  return sizeof(RedHeader) + 2 * elems * acc + 64;
+}
+
+int rua_segment_reduce(const void* data, const int64_t* off, int64_t N, int64_t S, int64_t H, int32_t dtype,
+                       int32_t op, void* out, void* ws, size_t ws_bytes, rua_stream_t stream) {
+  if (N < 0 || S < 0 || H < 0) return RUA_ERR_INVALID;
+  if (S == 0 || H == 0) return RUA_OK;
+  if (!off || !out || !ws || (N > 0 && !data)) return RUA_ERR_INVALID;
+  if (op < RUA_SUM || op > RUA_LOGSUMEXP) return RUA_ERR_INVALID;
+  if (dtype < RUA_F32 || dtype > RUA_BF16) return RUA_ERR_UNSUPPORTED;
+  RedPlan p = plan_reduce(N, H, dtype, op, data, out);
+  size_t acc = dtype == RUA_F64 ? 8 : 4;
+  if (ws_bytes < sizeof(RedHeader) + 2 * p.part_elems * acc) return RUA_ERR_WORKSPACE;
+  if (((uintptr_t)ws & 15u) != 0) return RUA_ERR_INVALID;
+  cudaStream_t st = (cudaStream_t)stream;
+  switch (dtype) {
+    case RUA_F32: return dispatch_vec<float>(op, p, data, off, N, S, H, out, ws, st);
+    case RUA_F64: return dispatch_vec<double>(op, p, data, off, N, S, H, out, ws, st);
+    case RUA_F16: return dispatch_vec<__half>(op, p, data, off, N, S, H, out, ws, st);
+    default: return dispatch_vec<__nv_bfloat16>(op, p, data, off, N, S, H, out, ws, st);
+  }
+}
+
+}  // extern "C"

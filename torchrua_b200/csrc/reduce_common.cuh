@@ -1,0 +1,162 @@
+// Shared numeric helpers of the segment-reduce kernels (forward: reduce.cu, backward: reduce_bwd.cu).
+#pragma once
+
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+#include <math_constants.h>
+
+#include "common.cuh"
+
+namespace rua {
+
+constexpr int kRedThreads = 128;
+constexpr int kRedUnroll = 8;
+
+// ---------------------------------------------------------------------------------------------
+// storage <-> accumulator conversion, 16-byte vectors
+// ---------------------------------------------------------------------------------------------
+template <typename T> struct Store;
+template <> struct Store<float> {
+  using Acc = float;
+  static constexpr int kVec = 4;
+  __device__ static void unpack(const uint4& r, Acc* x) {
+    x[0] = __uint_as_float(r.x); x[1] = __uint_as_float(r.y); x[2] = __uint_as_float(r.z); x[3] = __uint_as_float(r.w);
+  }
+  __device__ static uint4 pack(const Acc* x) {
+    return make_uint4(__float_as_uint(x[0]), __float_as_uint(x[1]), __float_as_uint(x[2]), __float_as_uint(x[3]));
+  }
+  __device__ static Acc to_acc(float v) { return v; }
+  __device__ static float from_acc(Acc v) { return v; }
+};
+template <> struct Store<double> {
+  using Acc = double;
+  static constexpr int kVec = 2;
+  __device__ static void unpack(const uint4& r, Acc* x) {
+    x[0] = __hiloint2double((int)r.y, (int)r.x);
+    x[1] = __hiloint2double((int)r.w, (int)r.z);
+  }
+  __device__ static uint4 pack(const Acc* x) {
+    return make_uint4((uint32_t)__double2loint(x[0]), (uint32_t)__double2hiint(x[0]),
+                      (uint32_t)__double2loint(x[1]), (uint32_t)__double2hiint(x[1]));
+  }
+  __device__ static Acc to_acc(double v) { return v; }
+  __device__ static double from_acc(Acc v) { return v; }
+};
+template <> struct Store<__half> {
+  using Acc = float;
+  static constexpr int kVec = 8;
+  __device__ static void unpack(const uint4& r, Acc* x) {
+    const uint32_t w[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      float2 f = __half22float2(*reinterpret_cast<const __half2*>(&w[k]));
+      x[2 * k] = f.x; x[2 * k + 1] = f.y;
+    }
+  }
+  __device__ static uint4 pack(const Acc* x) {
+    uint32_t w[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      __half2 h = __floats2half2_rn(x[2 * k], x[2 * k + 1]);
+      w[k] = *reinterpret_cast<uint32_t*>(&h);
+    }
+    return make_uint4(w[0], w[1], w[2], w[3]);
+  }
+  __device__ static Acc to_acc(__half v) { return __half2float(v); }
+  __device__ static __half from_acc(Acc v) { return __float2half_rn(v); }
+};
+template <> struct Store<__nv_bfloat16> {
+  using Acc = float;
+  static constexpr int kVec = 8;
+  __device__ static void unpack(const uint4& r, Acc* x) {
+    const uint32_t w[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {  // bf16 -> fp32 is a 16-bit shift
+      x[2 * k] = __uint_as_float(w[k] << 16);
+      x[2 * k + 1] = __uint_as_float(w[k] & 0xffff0000u);
+    }
+  }
+  __device__ static uint4 pack(const Acc* x) {
+    uint32_t w[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      __nv_bfloat162 h = __floats2bfloat162_rn(x[2 * k], x[2 * k + 1]);
+      w[k] = *reinterpret_cast<uint32_t*>(&h);
+    }
+    return make_uint4(w[0], w[1], w[2], w[3]);
+  }
+  __device__ static Acc to_acc(__nv_bfloat16 v) { return __bfloat162float(v); }
+  __device__ static __nv_bfloat16 from_acc(Acc v) { return __float2bfloat16_rn(v); }
+};
+
+// ---------------------------------------------------------------------------------------------
+// scalar math on the accumulator type
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ float max_nan(float a, float b) {  // NaN-propagating, like ATen's segment max
+  float r;
+  asm("max.NaN.f32 %0, %1, %2;" : "=f"(r) : "f"(a), "f"(b));
+  return r;
+}
+__device__ __forceinline__ float min_nan(float a, float b) {
+  float r;
+  asm("min.NaN.f32 %0, %1, %2;" : "=f"(r) : "f"(a), "f"(b));
+  return r;
+}
+__device__ __forceinline__ double max_nan(double a, double b) { return (a != a) ? a : ((b != b) ? b : (a < b ? b : a)); }
+__device__ __forceinline__ double min_nan(double a, double b) { return (a != a) ? a : ((b != b) ? b : (b < a ? b : a)); }
+__device__ __forceinline__ float min_num(float a, float b) { return fminf(a, b); }    // ignores NaN
+__device__ __forceinline__ float max_num(float a, float b) { return fmaxf(a, b); }
+__device__ __forceinline__ double min_num(double a, double b) { return fmin(a, b); }
+__device__ __forceinline__ double max_num(double a, double b) { return fmax(a, b); }
+template <typename A> __device__ __forceinline__ A inf_of();
+template <> __device__ __forceinline__ float inf_of<float>() { return CUDART_INF_F; }
+template <> __device__ __forceinline__ double inf_of<double>() { return CUDART_INF; }
+template <typename A> __device__ __forceinline__ A nan_of();
+template <> __device__ __forceinline__ float nan_of<float>() { return CUDART_NAN_F; }
+template <> __device__ __forceinline__ double nan_of<double>() { return CUDART_NAN; }
+template <bool kFast> __device__ __forceinline__ float exp_acc(float x) { return kFast ? __expf(x) : expf(x); }
+template <bool kFast> __device__ __forceinline__ double exp_acc(double x) { return exp(x); }
+__device__ __forceinline__ float log_acc(float x) { return logf(x); }
+__device__ __forceinline__ double log_acc(double x) { return log(x); }
+__device__ __forceinline__ float abs_acc(float x) { return fabsf(x); }
+__device__ __forceinline__ double abs_acc(double x) { return fabs(x); }
+
+// order-preserving integer keys so the global extreme can be reduced with integer atomics
+__device__ __forceinline__ unsigned long long order_key(float f) {
+  uint32_t b = __float_as_uint(f);
+  return (unsigned long long)((b & 0x80000000u) ? ~b : (b | 0x80000000u));
+}
+__device__ __forceinline__ unsigned long long order_key(double d) {
+  unsigned long long b = (unsigned long long)__double_as_longlong(d);
+  return (b & 0x8000000000000000ull) ? ~b : (b | 0x8000000000000000ull);
+}
+__device__ __forceinline__ float key_to(float, unsigned long long k) {
+  uint32_t b = (uint32_t)k;
+  return __uint_as_float((b & 0x80000000u) ? (b & 0x7fffffffu) : ~b);
+}
+__device__ __forceinline__ double key_to(double, unsigned long long k) {
+  return __longlong_as_double((long long)((k & 0x8000000000000000ull) ? (k & 0x7fffffffffffffffull) : ~k));
+}
+
+// raw (unconverted) register image of V storage elements: keeps the 8-deep load pipeline at 4
+// registers per row instead of V accumulator-typed ones
+template <typename T, int V> struct Raw { uint4 r; };
+template <typename T> struct Raw<T, 1> { T r; };
+template <typename T, int V>
+__device__ __forceinline__ void load_raw(const T* p, Raw<T, V>& w) {
+  if constexpr (V == 1) w.r = *p;
+  else w.r = __ldcs(reinterpret_cast<const uint4*>(p));
+}
+template <typename T, int V>
+__device__ __forceinline__ void unpack_raw(const Raw<T, V>& w, typename Store<T>::Acc* x) {
+  if constexpr (V == 1) x[0] = Store<T>::to_acc(w.r);
+  else Store<T>::unpack(w.r, x);
+}
+template <typename T, int V>
+__device__ __forceinline__ void store_vec(T* p, const typename Store<T>::Acc* x) {
+  if constexpr (V == 1) *p = Store<T>::from_acc(x[0]);
+  else *reinterpret_cast<uint4*>(p) = Store<T>::pack(x);
+}
+
+
+}  // namespace rua

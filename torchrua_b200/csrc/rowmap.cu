@@ -1,0 +1,335 @@
+// K1/K2 -- ragged row map: one kernel for the 12 layout conversions, head/last/rev/roll/trunc and
+// all of their backward passes.
+//
+// Replaces (reference file:line): to_cat core/cast.py:8-16, cat_pack_to_left :19-23, right_to_left
+// :26-32, to_pack :41-49, cat_pack_to_right :52-56, left_to_right :59-65, the (batch_ptr, token_ptr)
+// branches of core/get.py:21-79 and core/set.py:23-92, select/head.py:6-67, last.py:7-13,
+// rev.py:6-41, roll.py:6-37, trunc.py:9-62, reduce.py:64-69.
+//
+// The reference materialises ptr() index tensors (16*N bytes), a BxT int64 mask and a full
+// `new_full` of the padded output before a generic aten::index / index_put_ moves the payload.
+// Here the destination is walked ONCE in storage order; each warp decodes 32 destination rows in
+// parallel (one lane per row: binary search in the L1/L2-resident offset arrays), then the whole
+// warp moves those rows with 128-bit coalesced loads/stores, 4 independent vectors in flight per
+// lane.  Padding is written by the same pass, so every output byte is stored exactly once and no
+// payload byte is read twice: traffic = N*D read + rows_dst*D written (+ metadata).
+// HBM-bound; no shared memory (no reuse) and no tensor cores (nothing to contract).
+#include "common.cuh"
+
+namespace rua {
+
+struct RowMapParams {
+  const uint8_t* src;
+  uint8_t* dst;
+  int64_t row_vecs;   // vectors per row
+  rua_ragged_t rg;
+  rua_side_t s;       // source side
+  rua_side_t d;       // destination side
+  int32_t tmap;
+  int64_t tmap_arg;
+  int32_t pad_mode;
+  uint4 fill;         // fill pattern replicated to 16 bytes
+  int32_t rows_per_warp;   // power of two <= 32
+  int32_t lanes_per_row;   // power of two <= 32
+  int32_t col_splits;      // gridDim.y
+  const int64_t* gather_index;   // explicit source rows (rua_gather_rows) or NULL
+  const int64_t* scatter_index;  // explicit destination rows (rua_scatter_rows) or NULL
+};
+
+constexpr int64_t kPadRow = -1;
+constexpr int64_t kNoRow = -2;
+
+__device__ __forceinline__ int64_t side_len(const rua_side_t& sd, int64_t base_len) {
+  if (sd.len_xform == RUA_LEN_SAME) return base_len;
+  if (sd.len_xform == RUA_LEN_CONST) return sd.len_arg;
+  return base_len - sd.len_arg;
+}
+
+struct CatOff {  // exclusive prefix sum of the transformed lengths, in closed form
+  const int64_t* __restrict__ off;
+  int32_t xform;
+  int64_t arg;
+  __device__ __forceinline__ int64_t operator()(int64_t i) const {
+    if (xform == RUA_LEN_SAME) return __ldg(off + i);
+    if (xform == RUA_LEN_CONST) return arg * i;
+    return __ldg(off + i) - arg * i;
+  }
+};
+
+struct PackOff {  // trunc drops the first `shift` time steps of batch_sizes (select/trunc.py:42)
+  const int64_t* __restrict__ poff;
+  int64_t shift;
+  __device__ __forceinline__ int64_t operator()(int64_t t) const {
+    return __ldg(poff + t + shift) - __ldg(poff + shift);
+  }
+};
+
+__device__ __forceinline__ int64_t pack_shift(const rua_side_t& sd) {
+  return sd.len_xform == RUA_LEN_MINUS ? sd.len_arg : 0;
+}
+
+// destination row j -> source row (or kPadRow)
+__device__ __forceinline__ int64_t map_row(const RowMapParams& p, int64_t j) {
+  const rua_ragged_t& rg = p.rg;
+  int64_t i, td;
+  bool have_len = false;
+  int64_t base_len = 0;
+  if (p.d.layout == RUA_CAT) {
+    CatOff f{rg.off, p.d.len_xform, p.d.len_arg};
+    i = owner_search(f, rg.B, j);
+    td = j - f(i);
+  } else if (p.d.layout == RUA_PACK) {
+    int64_t sh = pack_shift(p.d);
+    PackOff f{rg.poff, sh};
+    int64_t steps = p.d.len_xform == RUA_LEN_CONST ? p.d.len_arg : rg.Tp - sh;
+    td = owner_search(f, steps, j);
+    i = __ldg(rg.sorted + (j - f(td)));
+  } else {
+    int64_t w = p.d.width;
+    if (p.d.rows < (1ll << 31)) {
+      uint32_t q = (uint32_t)j / (uint32_t)w;
+      i = q;
+      td = (uint32_t)j - q * (uint32_t)w;
+    } else {
+      i = j / w;
+      td = j - i * w;
+    }
+    base_len = __ldg(rg.off + i + 1) - __ldg(rg.off + i);
+    have_len = true;
+    int64_t ld = side_len(p.d, base_len);
+    if (p.d.layout == RUA_RIGHT) td -= (w - ld);
+    if (td < 0 || td >= ld) return kPadRow;
+  }
+  if (!have_len) base_len = __ldg(rg.off + i + 1) - __ldg(rg.off + i);
+
+  int64_t ts;
+  if (p.tmap == RUA_MAP_SHIFT) {
+    ts = td + p.tmap_arg;
+  } else if (p.tmap == RUA_MAP_REV) {
+    ts = base_len - 1 - td;
+  } else {
+    int64_t m = (td - p.tmap_arg) % base_len;  // base_len > 0 here: a row exists
+    ts = m < 0 ? m + base_len : m;
+  }
+  int64_t ls = side_len(p.s, base_len);
+  if (ts < 0 || ts >= ls) return kPadRow;
+
+  switch (p.s.layout) {
+    case RUA_CAT: {
+      CatOff f{rg.off, p.s.len_xform, p.s.len_arg};
+      return f(i) + ts;
+    }
+    case RUA_LEFT:
+      return i * p.s.width + ts;
+    case RUA_RIGHT:
+      return i * p.s.width + (p.s.width - ls) + ts;
+    default: {
+      int64_t sh = pack_shift(p.s);
+      PackOff f{rg.poff, sh};
+      return f(ts) + __ldg(rg.unsorted + i);
+    }
+  }
+}
+
+template <typename V> __device__ __forceinline__ V ld_stream(const V* p) { return __ldcs(p); }
+template <typename V> __device__ __forceinline__ void st_stream(V* p, V v) { __stcs(p, v); }
+
+// the fill pattern is replicated over 16 bytes; a vector narrower than the element (possible only
+// for oddly aligned views) picks the slice that matches its byte offset within the row
+__device__ __forceinline__ uint32_t fill_word(const uint4& f, int w) {
+  return w == 0 ? f.x : (w == 1 ? f.y : (w == 2 ? f.z : f.w));
+}
+template <typename V> __device__ __forceinline__ V make_fill(const uint4& f, int64_t byte_off);
+template <> __device__ __forceinline__ uint4 make_fill<uint4>(const uint4& f, int64_t) { return f; }
+template <> __device__ __forceinline__ uint2 make_fill<uint2>(const uint4& f, int64_t o) {
+  int w = (int)((o >> 2) & 2);
+  return make_uint2(fill_word(f, w), fill_word(f, w + 1));
+}
+template <> __device__ __forceinline__ unsigned int make_fill<unsigned int>(const uint4& f, int64_t o) {
+  return fill_word(f, (int)((o >> 2) & 3));
+}
+template <> __device__ __forceinline__ unsigned short make_fill<unsigned short>(const uint4& f, int64_t o) {
+  return (unsigned short)((fill_word(f, (int)((o >> 2) & 3)) >> (8 * (int)(o & 2))) & 0xffffu);
+}
+template <> __device__ __forceinline__ unsigned char make_fill<unsigned char>(const uint4& f, int64_t o) {
+  return (unsigned char)((fill_word(f, (int)((o >> 2) & 3)) >> (8 * (int)(o & 3))) & 0xffu);
+}
+
+constexpr int kRowMapThreads = 128;
+constexpr int kUnroll = 4;
+
+template <typename V>
+__global__ void __launch_bounds__(kRowMapThreads)
+row_map_kernel(const RowMapParams p) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = (int64_t)blockIdx.x * (kRowMapThreads / 32) + (threadIdx.x >> 5);
+  const int rpw = p.rows_per_warp;
+  const int64_t rows = p.d.rows;
+  const int64_t j0 = warp * rpw;
+  if (j0 >= rows) return;
+
+  // phase 1: one lane per destination row decodes where its bytes come from
+  int64_t srow = kNoRow, drow = kNoRow;
+  {
+    int64_t j = j0 + lane;
+    if (lane < rpw && j < rows) {
+      // explicit index tensors follow torch semantics: negative entries wrap around
+      if (p.gather_index) { srow = __ldg(p.gather_index + j); if (srow < 0) srow += p.s.rows; drow = j; }
+      else if (p.scatter_index) { srow = j; drow = __ldg(p.scatter_index + j); if (drow < 0) drow += p.s.rows; }
+      else { srow = map_row(p, j); drow = j; }
+      if (srow == kPadRow && p.pad_mode == RUA_PAD_ROW0) srow = 0;
+    }
+  }
+
+  // phase 2: the warp moves the rows; `lpr` lanes cooperate on one row, 32/lpr rows at a time
+  const int lpr = p.lanes_per_row;
+  const int groups = 32 / lpr;
+  const int g = lane / lpr, l = lane - g * lpr;
+  // column range of this CTA row (gridDim.y splits very wide rows across CTAs)
+  const int64_t cols_per = ceil_div(p.row_vecs, (int64_t)p.col_splits);
+  const int64_t c0 = (int64_t)blockIdx.y * cols_per;
+  const int64_t c1 = c0 + cols_per < p.row_vecs ? c0 + cols_per : p.row_vecs;
+  const V* __restrict__ src = reinterpret_cast<const V*>(p.src);
+  V* __restrict__ dst = reinterpret_cast<V*>(p.dst);
+
+  for (int r0 = 0; r0 < rpw; r0 += groups) {
+    const int r = r0 + g;
+    const int64_t s = shfl_i64(srow, r & 31);
+    const int64_t dj = shfl_i64(drow, r & 31);
+    if (r >= rpw || s == kNoRow) continue;
+    V* drow_p = dst + dj * p.row_vecs;
+    if (s >= 0) {
+      const V* srow_p = src + s * p.row_vecs;
+      int64_t c = c0 + l;
+      for (; c + (int64_t)(kUnroll - 1) * lpr < c1; c += (int64_t)kUnroll * lpr) {
+        V v[kUnroll];
+#pragma unroll
+        for (int u = 0; u < kUnroll; ++u) v[u] = ld_stream(srow_p + c + (int64_t)u * lpr);
+#pragma unroll
+        for (int u = 0; u < kUnroll; ++u) st_stream(drow_p + c + (int64_t)u * lpr, v[u]);
+      }
+      for (; c < c1; c += lpr) st_stream(drow_p + c, ld_stream(srow_p + c));
+    } else {
+      for (int64_t c = c0 + l; c < c1; c += lpr)
+        st_stream(drow_p + c, make_fill<V>(p.fill, c * (int64_t)sizeof(V)));
+    }
+  }
+}
+
+inline int pow2_floor(int64_t x) {
+  int p = 1;
+  while ((int64_t)p * 2 <= x) p *= 2;
+  return p;
+}
+
+static int launch_row_map(RowMapParams& p, int64_t row_bytes, int64_t rows, cudaStream_t st) {
+  if (rows <= 0 || row_bytes <= 0) return RUA_OK;
+  // widest vector that divides the row size and both base addresses
+  uintptr_t a = (uintptr_t)p.src | (uintptr_t)p.dst | (uintptr_t)row_bytes;
+  int vec = 16;
+  while (vec > 1 && (a & (uintptr_t)(vec - 1))) vec >>= 1;
+  p.row_vecs = row_bytes / vec;
+
+  // lanes per row: short rows share a warp (32/lpr rows move concurrently)
+  int lpr = 1;
+  while (lpr < 32 && lpr < p.row_vecs) lpr <<= 1;  // smallest power of two covering the row, <= 32
+  p.lanes_per_row = lpr;
+
+  // rows per warp / column splits: keep >= ~32 warps per SM in flight when the problem allows it
+  const int64_t target_warps = (int64_t)kNumSMs * 32;
+  int rpw = 32;
+  while (rpw > 32 / lpr && rpw > 1 && ceil_div(rows, rpw) < target_warps) rpw >>= 1;
+  p.rows_per_warp = rpw;
+  int64_t warps = ceil_div(rows, rpw);
+  int splits = 1;
+  while (warps * splits < target_warps && p.row_vecs / (splits * 2) >= 32 * kUnroll && splits < 64) splits *= 2;
+  p.col_splits = splits;
+
+  int64_t blocks = ceil_div(warps, kRowMapThreads / 32);
+  if (blocks >= (1ll << 31)) return RUA_ERR_UNSUPPORTED;
+  dim3 grid((unsigned)blocks, (unsigned)splits);
+  switch (vec) {
+    case 16: row_map_kernel<uint4><<<grid, kRowMapThreads, 0, st>>>(p); break;
+    case 8: row_map_kernel<uint2><<<grid, kRowMapThreads, 0, st>>>(p); break;
+    case 4: row_map_kernel<unsigned int><<<grid, kRowMapThreads, 0, st>>>(p); break;
+    case 2: row_map_kernel<unsigned short><<<grid, kRowMapThreads, 0, st>>>(p); break;
+    default: row_map_kernel<unsigned char><<<grid, kRowMapThreads, 0, st>>>(p); break;
+  }
+  return check_launch();
+}
+
+static bool valid_side(const rua_side_t* s) {
+  if (!s) return false;
+  if (s->layout < RUA_CAT || s->layout > RUA_RIGHT) return false;
+  if (s->len_xform < RUA_LEN_SAME || s->len_xform > RUA_LEN_MINUS) return false;
+  if ((s->layout == RUA_LEFT || s->layout == RUA_RIGHT) && s->width <= 0 && s->rows > 0) return false;
+  return s->rows >= 0;
+}
+
+}  // namespace rua
+
+using namespace rua;
+
+extern "C" {
+
+int rua_row_map(const void* src, void* dst, int64_t row_bytes, const rua_ragged_t* ragged,
+                const rua_side_t* src_side, const rua_side_t* dst_side, int32_t tmap, int64_t tmap_arg,
+                int32_t pad_mode, const void* fill_host, int32_t fill_bytes, rua_stream_t stream) {
+  if (!ragged || !valid_side(src_side) || !valid_side(dst_side) || row_bytes < 0) return RUA_ERR_INVALID;
+  if (dst_side->rows == 0 || row_bytes == 0) return RUA_OK;
+  if (!dst || !ragged->off || ragged->B <= 0) return RUA_ERR_INVALID;
+  if (tmap < RUA_MAP_SHIFT || tmap > RUA_MAP_ROLL) return RUA_ERR_INVALID;
+  if (pad_mode != RUA_PAD_FILL && pad_mode != RUA_PAD_ROW0) return RUA_ERR_INVALID;
+  bool uses_pack = src_side->layout == RUA_PACK || dst_side->layout == RUA_PACK;
+  if (uses_pack && (!ragged->poff || !ragged->sorted || !ragged->unsorted)) return RUA_ERR_INVALID;
+  if (!src && src_side->rows > 0) return RUA_ERR_INVALID;
+  if (fill_bytes != 0 && fill_bytes != 1 && fill_bytes != 2 && fill_bytes != 4 && fill_bytes != 8 &&
+      fill_bytes != 16)
+    return RUA_ERR_INVALID;
+  if (fill_bytes > 0 && (!fill_host || row_bytes % fill_bytes != 0)) return RUA_ERR_INVALID;
+
+  RowMapParams p{};
+  p.src = (const uint8_t*)src;
+  p.dst = (uint8_t*)dst;
+  p.rg = *ragged;
+  p.s = *src_side;
+  p.d = *dst_side;
+  p.tmap = tmap;
+  p.tmap_arg = tmap_arg;
+  p.pad_mode = pad_mode;
+  uint8_t pat[16] = {0};
+  if (fill_bytes > 0)
+    for (int k = 0; k < 16; ++k) pat[k] = ((const uint8_t*)fill_host)[k % fill_bytes];
+  p.fill = make_uint4(((uint32_t*)pat)[0], ((uint32_t*)pat)[1], ((uint32_t*)pat)[2], ((uint32_t*)pat)[3]);
+  p.gather_index = nullptr;
+  p.scatter_index = nullptr;
+  return launch_row_map(p, row_bytes, dst_side->rows, (cudaStream_t)stream);
+}
+
+static int index_rows(const void* src, const int64_t* gidx, const int64_t* sidx, int64_t n, int64_t indexed_rows,
+                      int64_t row_bytes, void* dst, rua_stream_t stream) {
+  if (n < 0 || row_bytes < 0 || indexed_rows < 0) return RUA_ERR_INVALID;
+  if (n == 0 || row_bytes == 0) return RUA_OK;
+  if (!src || !dst || (!gidx && !sidx)) return RUA_ERR_INVALID;
+  RowMapParams p{};
+  p.src = (const uint8_t*)src;
+  p.dst = (uint8_t*)dst;
+  p.d.rows = n;
+  p.s.rows = indexed_rows;  // size of the indexed side, for negative-index wrap-around
+  p.gather_index = gidx;
+  p.scatter_index = sidx;
+  p.pad_mode = RUA_PAD_FILL;
+  return launch_row_map(p, row_bytes, n, (cudaStream_t)stream);
+}
+
+int rua_gather_rows(const void* src, int64_t src_rows, const int64_t* index, int64_t n, int64_t row_bytes,
+                    void* dst, rua_stream_t stream) {
+  return index_rows(src, index, nullptr, n, src_rows, row_bytes, dst, stream);
+}
+
+int rua_scatter_rows(const void* src, const int64_t* index, int64_t n, int64_t row_bytes, void* dst,
+                     int64_t dst_rows, rua_stream_t stream) {
+  return index_rows(src, nullptr, index, n, dst_rows, row_bytes, dst, stream);
+}
+
+}  // extern "C"

@@ -60,7 +60,9 @@ enum rua_tmap {
 
 enum rua_pad {
   RUA_PAD_FILL = 0, /* padding / unmapped rows receive the fill pattern */
-  RUA_PAD_ROW0 = 1  /* ... receive a copy of flat source row 0 (L/R.roll quirk, select/roll.py:19-34) */
+  RUA_PAD_ROW0 = 1, /* ... receive a copy of flat source row 0 (L/R.roll quirk, select/roll.py:19-34) */
+  RUA_PAD_WRAP = 2  /* FILL, except that source position -1 wraps like a negative Python index: what
+                       last() / segment_last return for an EMPTY sequence (select/last.py:11-13)   */
 };
 
 enum rua_dtype { RUA_F32 = 0, RUA_F64 = 1, RUA_F16 = 2, RUA_BF16 = 3 };

@@ -346,6 +346,10 @@ def last(seq) -> np.ndarray:
     """torchrua/select/last.py:7-13: X[(arange(B), len-1)] -> plain (B,*) array."""
     lens = _lengths(seq)
     b = np.arange(lens.shape[0], dtype=I64)
+    if isinstance(seq, Cat):
+        # cat_getitem goes through C.offsets(), which is clamped to N-1 (layout/cat.py:81); an EMPTY
+        # sequence therefore reads row min(off, N-1) - 1, wrapping like any negative index
+        return seq.data[np.minimum(excl_scan(lens)[:-1], seq.data.shape[0] - 1) + lens - 1]
     return _raw(seq)[_rows(seq, b, lens - 1)]
 
 
@@ -461,8 +465,9 @@ def segment_head(data, sizes):
 
 
 def segment_last(data, sizes):
-    """reduce.py:68-69  last row of each (non-empty) segment."""
-    return data[excl_scan(np.asarray(sizes, dtype=I64))[1:] - 1]
+    """reduce.py:68-69  C(data, sizes).last(): last row of each segment; an EMPTY segment wraps to the
+    row before its (clamped) offset -- see last()."""
+    return last(Cat(data, np.asarray(sizes, dtype=I64)))
 
 
 REDUCERS = {

@@ -187,6 +187,7 @@ def main():
     sizes = torch.tensor([2, 0, 3, 0, 1, 6, 0], dtype=torch.long)
     data = torch.randn((int(sizes.sum()), 4), generator=g)
     reduce_case(rec, data, sizes, 'empty', with_head_last=False)
+    rec.put('empty.last', rua.segment_last(data, sizes), True)  # empty segments wrap to the previous row
     nan = data.clone()
     nan[4, 1] = float('nan')
     reduce_case(rec, nan, sizes, 'nan', with_head_last=False)

@@ -162,6 +162,11 @@ def test_segment_reduce(rua, tag, case, fns):
         check_reduce(g, f'{tag}.{fn}', got, fn, np.nan_to_num(data), sizes, rtol=1e-5 if data.dtype != np.float64 else 1e-12)
 
 
+def test_segment_last_empty_segments_wrap(rua):
+    g = Golden('reduce_edge')
+    g.check('empty.last', host(rua.segment_last(dev(g['empty.data']), dev(g['empty.sizes']))))
+
+
 def test_segment_reduce_bf16_contract(rua):
     """bf16: fp32 accumulation, rounded once; oracle = reference on the same values upcast to fp32
     (rtol 1e-2 per north_star; in practice max/min are exact and sums differ by at most 1 bf16 ulp)."""

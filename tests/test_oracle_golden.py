@@ -126,6 +126,11 @@ def test_segment_reduce(tag, case, fns):
             g.check(f'{tag}.{fn}', out)
 
 
+def test_segment_last_empty_segments_wrap():
+    g = Golden('reduce_edge')
+    g.check('empty.last', ora.segment_last(g['empty.data'], g['empty.sizes']))
+
+
 def test_segment_reduce_bf16_contract():
     """bf16 inputs: oracle = reference on the same values upcast to fp32, rounded once."""
     g = Golden('reduce_edge')

@@ -14,7 +14,7 @@ LIB_PATH = os.path.join(HERE, 'lib', 'librua_b200.so')
 CAT, LEFT, PACK, RIGHT = 0, 1, 2, 3
 LEN_SAME, LEN_CONST, LEN_MINUS = 0, 1, 2
 MAP_SHIFT, MAP_REV, MAP_ROLL = 0, 1, 2
-PAD_FILL, PAD_ROW0 = 0, 1
+PAD_FILL, PAD_ROW0, PAD_WRAP = 0, 1, 2
 F32, F64, F16, BF16 = 0, 1, 2, 3
 SUM, MEAN, PROD, MAX, MIN, LOGSUMEXP = 0, 1, 2, 3, 4, 5
 

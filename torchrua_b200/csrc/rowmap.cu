@@ -112,6 +112,17 @@ __device__ __forceinline__ int64_t map_row(const RowMapParams& p, int64_t j) {
     ts = m < 0 ? m + base_len : m;
   }
   int64_t ls = side_len(p.s, base_len);
+  if (p.pad_mode == RUA_PAD_WRAP && ts == -1) {
+    // last() of an EMPTY sequence in the reference indexes position len-1 = -1, which wraps
+    // (select/last.py:11-13): C reads row min(off[i], N-1) - 1 (mod N) because C.offsets() is clamped
+    // (layout/cat.py:81); L and R read the last column of row i (core/get.py:42,74).
+    if (p.s.layout == RUA_CAT) {
+      int64_t o = __ldg(rg.off + i);
+      o = (o < p.s.rows - 1 ? o : p.s.rows - 1) - 1;
+      return o < 0 ? o + p.s.rows : o;
+    }
+    if (p.s.layout == RUA_LEFT || p.s.layout == RUA_RIGHT) return i * p.s.width + p.s.width - 1;
+  }
   if (ts < 0 || ts >= ls) return kPadRow;
 
   switch (p.s.layout) {
@@ -279,7 +290,7 @@ int rua_row_map(const void* src, void* dst, int64_t row_bytes, const rua_ragged_
   if (dst_side->rows == 0 || row_bytes == 0) return RUA_OK;
   if (!dst || !ragged->off || ragged->B <= 0) return RUA_ERR_INVALID;
   if (tmap < RUA_MAP_SHIFT || tmap > RUA_MAP_ROLL) return RUA_ERR_INVALID;
-  if (pad_mode != RUA_PAD_FILL && pad_mode != RUA_PAD_ROW0) return RUA_ERR_INVALID;
+  if (pad_mode < RUA_PAD_FILL || pad_mode > RUA_PAD_WRAP) return RUA_ERR_INVALID;
   bool uses_pack = src_side->layout == RUA_PACK || dst_side->layout == RUA_PACK;
   if (uses_pack && (!ragged->poff || !ragged->sorted || !ragged->unsorted)) return RUA_ERR_INVALID;
   if (!src && src_side->rows > 0) return RUA_ERR_INVALID;

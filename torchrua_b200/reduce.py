@@ -8,7 +8,7 @@ index reductions, SURVEY.md 8f "next" row 1) and still compose ATen ops exactly 
 import torch
 
 from torchrua_b200 import _native
-from torchrua_b200._lib import CAT, LEN_CONST, MAP_REV, MAP_SHIFT
+from torchrua_b200._lib import CAT, LEN_CONST, MAP_REV, MAP_SHIFT, PAD_FILL, PAD_WRAP
 from torchrua_b200._native import MapSpec, SideSpec
 from torchrua_b200.layout import T
 
@@ -70,7 +70,7 @@ def _segment_pick(tensor: T, segment_sizes: T, last: bool) -> T:
     rg = _native.ragged_from_lengths(segment_sizes)
     spec = MapSpec(rg=rg, src=SideSpec(CAT, rows=tensor.size()[0]),
                    dst=SideSpec(CAT, xform=LEN_CONST, arg=1, rows=rg.B),
-                   tmap=MAP_REV if last else MAP_SHIFT)
+                   tmap=MAP_REV if last else MAP_SHIFT, pad_mode=PAD_WRAP if last else PAD_FILL)
     return _native.row_map(tensor, spec)
 
 

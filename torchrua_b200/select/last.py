@@ -3,7 +3,7 @@ torchrua/select/last.py:7-13; one row-map launch moving B rows (no cat_view mask
 from torch import Tensor
 
 from torchrua_b200 import _native
-from torchrua_b200._lib import CAT, LEN_CONST, MAP_REV
+from torchrua_b200._lib import CAT, LEN_CONST, MAP_REV, PAD_WRAP
 from torchrua_b200._native import MapSpec, SideSpec
 from torchrua_b200.core.cast import side_of
 from torchrua_b200.layout import C, L, P, R, Z
@@ -11,7 +11,8 @@ from torchrua_b200.layout import C, L, P, R, Z
 
 def last(self: Z) -> Tensor:
     rg = self._ragged()
-    spec = MapSpec(rg=rg, src=side_of(self, rg), dst=SideSpec(CAT, xform=LEN_CONST, arg=1, rows=rg.B), tmap=MAP_REV)
+    spec = MapSpec(rg=rg, src=side_of(self, rg), dst=SideSpec(CAT, xform=LEN_CONST, arg=1, rows=rg.B), tmap=MAP_REV,
+                   pad_mode=PAD_WRAP)
     return _native.row_map(self.raw(), spec)
 
 

@@ -1,0 +1,360 @@
+#!/usr/bin/env python
+"""bench.py -- tokens/s and achieved HBM GB/s of the ragged-sequence hot path on N B200s.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
+        bench.py --gpus N --steps K --warmup W
+
+Workload (per GPU): BASELINE.json configs[1] -- batch 4096, lengths U[1,512], hidden 1024 bf16
+(N ~ 1.06 M tokens, 2.17 GB per ragged layout, 4.29 GB per padded layout: far larger than the 126 MB L2).
+One STEP is one pass of the hot path over the batch:
+
+    C -> P (pack)  ->  L (left pad)  ->  R (right pad)  ->  C (cat)  +  segment_sum  +  segment_max
+
+i.e. 4 layout conversions (one rua_row_map launch each, plus their metadata kernels) and 2 segment
+reductions, every step recomputing all metadata (the per-tensor metadata cache is cleared each step).
+`value` = tokens through the whole step per second, summed over GPUs (weak scaling: per-GPU work fixed).
+
+Prints ONE JSON line (see the keys at the bottom).  `--impl reference` times the CPU restatement of the
+reference's path (oracle/rua_oracle.c, OpenMP over all host threads) on a bounded sample instead.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+BATCH = 4096
+MAX_LEN = 512
+HIDDEN = 1024
+METRIC = 'tokens/sec through pack/pad/cat + segment reduce (C->P->L->R->C + segment_sum + segment_max)'
+WORKLOAD = 'configs[1]: pack/pad/cat conversions, batch 4096, lengths U[1,512], hidden 1024 bf16'
+
+
+def workload_lengths(world: int):
+    import torch
+    g = torch.Generator().manual_seed(0)
+    return torch.randint(1, MAX_LEN + 1, (BATCH * world,), generator=g)
+
+
+# --------------------------------------------------------------------------------------------------
+# CPU baseline: the oracle port, all host threads, on a bounded sample of the same workload
+# --------------------------------------------------------------------------------------------------
+def cpu_pipeline_factory(n_seq: int):
+    import numpy as np
+    import torch
+    from oracle import c_oracle as co
+    lens = workload_lengths(1)[:n_seq].numpy()
+    n = int(lens.sum())
+    g = torch.Generator().manual_seed(1)
+    data = torch.randn((n, HIDDEN), generator=g).to(torch.bfloat16).view(torch.uint16).numpy()
+
+    def step():
+        bs, srt, uns = co.pack_meta(lens)
+        p = co.move(data, 'C', 'P', lens, bs, uns)
+        left = co.move(p, 'P', 'L', lens, bs, uns, fill=0)
+        right = co.move(left, 'L', 'R', lens, fill=0)
+        back = co.move(right, 'R', 'C', lens)
+        s = co.segment_reduce(back, lens, 'sum', bf16=True)
+        m = co.segment_reduce(back, lens, 'max', bf16=True)
+        return back, s, m
+
+    return step, n, data
+
+
+def time_cpu(steps: int, warmup: int, budget_s: float):
+    """returns (tokens_per_s, ms_per_step, n_seq, n_tokens, threads)"""
+    from oracle import c_oracle as co
+    co.build()
+    n_seq = 512
+    while True:
+        step, n_tok, _ = cpu_pipeline_factory(n_seq)
+        t0 = time.perf_counter()
+        step()
+        one = time.perf_counter() - t0
+        if one * (steps + warmup) <= budget_s or n_seq <= 32:
+            break
+        n_seq //= 2
+    for _ in range(max(warmup - 1, 0)):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        step()
+    dt = time.perf_counter() - t0
+    return n_tok * steps / dt, dt / steps * 1e3, n_seq, n_tok, co.num_threads()
+
+
+# --------------------------------------------------------------------------------------------------
+# clocks sampler (nvidia-smi during the timed region)
+# --------------------------------------------------------------------------------------------------
+class Clocks:
+    QUERY = ('index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,'
+             'clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,'
+             'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, index: int):
+        self.index = index
+        self.path = tempfile.mktemp(prefix='rua_clocks_', suffix='.csv')
+        self.proc = None
+
+    def start(self):
+        try:
+            self.fp = open(self.path, 'w')
+            self.proc = subprocess.Popen(['nvidia-smi', f'--query-gpu={self.QUERY}', '--format=csv,noheader,nounits',
+                                          '-i', str(self.index), '-lms', '100'], stdout=self.fp,
+                                         stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        out = {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': [], 'samples': 0}
+        if self.proc is None:
+            return out
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        self.fp.close()
+        sm, mx, reasons = [], [], set()
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        for line in open(self.path):
+            f = [x.strip() for x in line.split(',')]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, val in zip(names, f[5:9]):
+                if val.lower().startswith('active'):
+                    reasons.add(name)
+        try:
+            os.unlink(self.path)
+        except OSError:
+            pass
+        if sm:
+            busy = sorted(sm)[len(sm) // 2:]      # upper half = samples taken under load
+            out.update(sm_mhz=statistics.median(busy), sm_max_mhz=max(mx), reasons=sorted(reasons), samples=len(sm))
+        return out
+
+
+# --------------------------------------------------------------------------------------------------
+# reference arm
+# --------------------------------------------------------------------------------------------------
+def run_reference(args):
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return
+    tps, ms, n_seq, n_tok, threads = time_cpu(args.steps, max(args.warmup, 1), budget_s=150.0)
+    sample = f'first {n_seq} of the {BATCH} sequences ({n_tok} tokens, hidden {HIDDEN} bf16) per step'
+    line = {
+        'impl': 'reference', 'metric': METRIC, 'value': tps, 'unit': 'tokens/s', 'n_gpus': args.gpus,
+        'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms, 'higher_is_better': True, 'scaling': 'weak',
+        'vs_baseline': None, 'dtype': 'bf16', 'data': 'synthetic',
+        'config': {'workload': WORKLOAD, 'step': 'C->P->L->R->C + segment_sum + segment_max',
+                   'device': 'host CPU (no GPU work)', 'sample': sample},
+        'cpu_baseline': {'value': tps, 'unit': 'tokens/s', 'cores': threads, 'kind': 'port', 'sample': sample,
+                         'what': 'oracle/rua_oracle.c: C restatement of the reference path, OpenMP over all host threads'},
+        'e2e': {'value': tps, 'unit': 'tokens/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+        'gpu_launches': 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# --------------------------------------------------------------------------------------------------
+# our arm
+# --------------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+
+    import torchrua_b200 as rua
+    from torchrua_b200 import _lib, _native, shard
+
+    rank = int(os.environ.get('RANK', '0'))
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    if world != args.gpus and world > 1:
+        raise SystemExit(f'--gpus {args.gpus} but WORLD_SIZE={world}')
+    torch.cuda.set_device(local)
+    dev = torch.device('cuda', local)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=dev)
+    lib = _lib.load()
+
+    # ---- synthetic batch, sharded by sequence with length-balanced partitioning --------------------
+    glens = workload_lengths(world)
+    parts = shard.balanced_partition(glens, world)
+    lens_host = glens[parts[rank]].contiguous()
+    n_tok = int(lens_host.sum())
+    total_tokens = int(glens.sum())
+    g = torch.Generator(device=dev).manual_seed(1 + rank)
+    data = torch.randn((n_tok, HIDDEN), generator=g, device=dev, dtype=torch.float32).to(torch.bfloat16)
+    lens = lens_host.to(dev)
+    cap = max(p.numel() for p in parts)
+    gathered = torch.empty((world, cap + 1), dtype=torch.long, device=dev) if world > 1 else None
+
+    def step(d, ln):
+        _native._CACHE.clear()                      # no metadata survives from one step to the next
+        if world > 1:                               # the only collective: 8 bytes per sequence of metadata
+            shard.all_gather_lengths_fixed(ln, cap, gathered)
+        c = rua.C(data=d, token_sizes=ln)
+        p = c.pack()
+        left = p.left(0)
+        right = left.right(0)
+        back = right.cat()
+        s = rua.segment_sum(back.data, back.token_sizes)
+        m = rua.segment_max(back.data, back.token_sizes)
+        return back, s, m
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- warm-up, then the device-timed region -----------------------------------------------------
+    for _ in range(max(args.warmup, 3)):
+        out = step(data, lens)
+    assert torch.equal(out[0].data, data), 'round trip C->P->L->R->C is not the identity'
+    del out
+    clocks = Clocks(local)
+    barrier()
+    clocks.start()
+    _native.PROFILE = []
+    launches0 = lib.rua_launch_count()
+    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0.record()
+    for _ in range(args.steps):
+        step(data, lens)
+    t1.record()
+    barrier()
+    launches = lib.rua_launch_count() - launches0
+    prof, _native.PROFILE = _native.PROFILE, None
+    clk = clocks.stop()
+    ms = torch.tensor([t0.elapsed_time(t1)], dtype=torch.double, device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms_total = float(ms)
+    value = total_tokens * args.steps / (ms_total * 1e-3)
+
+    # ---- per-kernel roofline from the events recorded inside the timed region ---------------------
+    per = {}
+    for name, a, b, nbytes in prof:
+        e = per.setdefault(name, [0.0, 0, 0])
+        e[0] += a.elapsed_time(b)
+        e[1] += nbytes
+        e[2] += 1
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json')))
+    except Exception:
+        pass
+    peak = float(peaks.get('hbm_gbs', 6650.0))
+    peak_src = 'measured (MEASURED_PEAKS.json hbm_gbs)' if 'hbm_gbs' in peaks else 'fallback 6.65 TB/s (B200_PROFILING.md)'
+    traffic = None
+    try:
+        traffic = json.load(open(os.path.join(ROOT, 'profiles', 'roofline_traffic.json'))).get('row_map_bytes_per_launch')
+    except Exception:
+        pass
+    rm = per.get('row_map', [1.0, 0, 1])
+    achieved = rm[1] / (rm[0] * 1e-3) / 1e9
+    roofline = {'bound': 'hbm', 'kernel': 'row_map_kernel<uint4> (4 launches per step: C->P, P->L, L->R, R->C)',
+                'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak, 'traffic': traffic,
+                'peak_source': peak_src, 'frac_of_nameplate_8000': achieved / 8000.0,
+                'algorithmic_bytes_per_launch': rm[1] / max(rm[2], 1), 'avg_launch_ms': rm[0] / max(rm[2], 1),
+                'share_of_step': rm[0] / ms_total}
+    sr = per.get('segment_reduce')
+    kernels = {'row_map': {'gbs': achieved, 'ms_per_launch': rm[0] / max(rm[2], 1), 'launches': rm[2]}}
+    if sr:
+        kernels['segment_reduce'] = {'gbs': sr[1] / (sr[0] * 1e-3) / 1e9, 'ms_per_launch': sr[0] / sr[2],
+                                     'launches': sr[2], 'share_of_step': sr[0] / ms_total}
+
+    # ---- end to end through the public API with HOST buffers (H2D + D2H inside the timed region) --
+    e2e_steps = max(2, min(args.steps, 5))
+    h_data = torch.empty((n_tok, HIDDEN), dtype=torch.bfloat16, pin_memory=True)
+    h_data.copy_(data)
+    h_lens = lens_host.pin_memory()
+    h_back = torch.empty((n_tok, HIDDEN), dtype=torch.bfloat16, pin_memory=True)
+    h_sum = torch.empty((lens_host.numel(), HIDDEN), dtype=torch.bfloat16, pin_memory=True)
+    h_max = torch.empty_like(h_sum)
+
+    def e2e_step():
+        d = h_data.to(dev, non_blocking=True)
+        ln = h_lens.to(dev, non_blocking=True)
+        back, s, m = step(d, ln)
+        h_back.copy_(back.data, non_blocking=True)
+        h_sum.copy_(s, non_blocking=True)
+        h_max.copy_(m, non_blocking=True)
+
+    e2e_step()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(e2e_steps):
+        e2e_step()
+    e1.record()
+    barrier()
+    assert torch.equal(h_back, h_data)
+    ems = torch.tensor([e0.elapsed_time(e1)], dtype=torch.double, device=dev)
+    if world > 1:
+        dist.all_reduce(ems, op=dist.ReduceOp.MAX)
+    e2e_value = total_tokens * e2e_steps / (float(ems) * 1e-3)
+    h2d = h_data.numel() * 2 + h_lens.numel() * 8
+    d2h = h_back.numel() * 2 + h_sum.numel() * 2 * 2
+
+    # ---- CPU baseline (rank 0, single-GPU run only) ------------------------------------------------
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        tps, cms, n_seq, cn, threads = time_cpu(steps=3, warmup=1, budget_s=25.0)
+        cpu = {'value': tps, 'unit': 'tokens/s', 'cores': threads, 'kind': 'port', 'ms_per_step': cms,
+               'sample': f'first {n_seq} of the {BATCH} sequences ({cn} tokens, hidden {HIDDEN} bf16), 3 steps',
+               'what': 'oracle/rua_oracle.c (C restatement of the reference path, OpenMP, all host threads)'}
+
+    if rank == 0:
+        line = {
+            'metric': METRIC, 'value': value, 'unit': 'tokens/s', 'n_gpus': world, 'steps': args.steps,
+            'warmup': max(args.warmup, 3), 'ms_per_step': ms_total / args.steps, 'higher_is_better': True,
+            'scaling': 'weak', 'vs_baseline': None, 'dtype': 'bf16', 'data': 'synthetic',
+            'config': {'workload': WORKLOAD, 'step': 'C->P->L->R->C + segment_sum + segment_max',
+                       'batch_per_gpu': BATCH, 'tokens_per_gpu': n_tok, 'tokens_total': total_tokens, 'hidden': HIDDEN,
+                       'l2': 'inputs larger than L2: 2.17 GB per ragged layout, 4.29 GB per padded layout vs 126 MB',
+                       'metadata': 'recomputed every step (cache cleared)',
+                       'parallelism': f'sequence-sharded x{world}, length-balanced (snake), lengths all-gather only'},
+            'roofline': roofline, 'kernels': kernels, 'cpu_baseline': cpu,
+            'e2e': {'value': e2e_value, 'unit': 'tokens/s', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h,
+                    'steps': e2e_steps, 'ms_per_step': float(ems) / e2e_steps,
+                    'what': 'pinned host C batch -> H2D -> same step through the public API -> D2H of the round-tripped '
+                            'C data, segment_sum and segment_max'},
+            'gpu_launches': int(launches), 'clocks': clk,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=20)
+    ap.add_argument('--warmup', type=int, default=5)
+    ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--no-cpu', action='store_true', help='skip the cpu_baseline leg')
+    args = ap.parse_args()
+    if args.impl == 'reference':
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == '__main__':
+    main()

@@ -41,6 +41,25 @@ def _stream() -> int:
     return torch.cuda.current_stream().cuda_stream
 
 
+# optional per-launch timing (bench.py sets PROFILE = [] to collect (name, start, end, algorithmic_bytes);
+# events are recorded on the launching stream right around the kernel launch)
+PROFILE = None
+
+
+def _profile_begin():
+    if PROFILE is None:
+        return None
+    ev = torch.cuda.Event(enable_timing=True)
+    ev.record()
+    return ev
+
+
+def _profile_end(start, name: str, nbytes: int) -> None:
+    end = torch.cuda.Event(enable_timing=True)
+    end.record()
+    PROFILE.append((name, start, end, nbytes))
+
+
 def _ptr(t: Optional[Tensor]) -> Optional[int]:
     return None if t is None else t.data_ptr()
 
@@ -289,9 +308,17 @@ def _row_map_raw(src: Tensor, spec: MapSpec, fill: bytes, feat: Tuple[int, ...],
     rg = spec.rg.c_struct()
     s, d = spec.src.c_struct(), spec.dst.c_struct()
     with torch.cuda.device(device):
+        prof = _profile_begin()
         _lib.check(lib.rua_row_map(_ptr(src), out.data_ptr(), row_bytes, ctypes.byref(rg), ctypes.byref(s),
                                    ctypes.byref(d), spec.tmap, spec.tmap_arg, spec.pad_mode, fill, len(fill),
                                    _stream()), 'rua_row_map')
+        if prof is not None:
+            # algorithmic bytes: every live token read once, every destination row
+            # written once, plus the int64 metadata the kernel consults
+            tokens = min(spec.src.rows, spec.dst.rows) if spec.rg._N is None else min(spec.rg._N, spec.src.rows,
+                                                                                      spec.dst.rows)
+            meta = 8 * spec.rg.B + (8 * spec.rg.Tp if PACK in (spec.src.layout, spec.dst.layout) else 0)
+            _profile_end(prof, 'row_map', tokens * row_bytes + rows * row_bytes + meta)
     return out
 
 
@@ -429,8 +456,11 @@ def _reduce_raw(data: Tensor, off: Tensor, S: int, op: int) -> Tensor:
     with torch.cuda.device(data.device):
         nbytes = lib.rua_segment_reduce_workspace_bytes(N, S, H, dt, op)
         ws = torch.empty(nbytes, dtype=torch.uint8, device=data.device)
+        prof = _profile_begin()
         _lib.check(lib.rua_segment_reduce(_ptr(data), off.data_ptr(), N, S, H, dt, op, out.data_ptr(), ws.data_ptr(),
                                           nbytes, _stream()), 'rua_segment_reduce')
+        if prof is not None:
+            _profile_end(prof, 'segment_reduce', (N + S) * H * data.element_size() + 8 * S)
     return out
 
 

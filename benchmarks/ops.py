@@ -1,0 +1,181 @@
+#!/usr/bin/env python
+"""Per-op timings of the hot path at BASELINE.json's configs 2, 3 and 5 on one B200 (not the contract bench:
+that is ../bench.py).  Every op is timed through the public API (metadata cache cleared before each call, so
+scans / sorts / host syncs are inside the number) with CUDA events, median of `--reps` after 2 warm-ups;
+`kernel` columns come from events recorded right around the dominant kernel launch.
+
+Also times, where one exists, the stock ATen *payload* op the reference would end up launching on the same
+GPU (advanced-index gather with a PRECOMPUTED index, `torch.segment_reduce`) -- a lower bound on the
+reference's GPU cost that leaves out its 130-450 ATen calls of index construction and 18-48 host syncs.
+
+    python benchmarks/ops.py [--cfg 2 3 5] [--reps 10] [--out gpurun_out/ops_r1.json]
+"""
+import argparse
+import json
+import os
+import statistics
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+import torchrua_b200 as rua  # noqa: E402
+from torchrua_b200 import _native  # noqa: E402
+
+PEAK = 6526.2
+try:
+    PEAK = float(json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json')))['hbm_gbs'])
+except Exception:
+    pass
+
+
+def timed(fn, reps, clear=True):
+    """median (api_ms, kernel_ms) of fn()."""
+    api, ker = [], []
+    for it in range(reps + 2):
+        if clear:
+            _native._CACHE.clear()
+        _native.PROFILE = []
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        a.record()
+        out = fn()
+        b.record()
+        torch.cuda.synchronize()
+        prof, _native.PROFILE = _native.PROFILE, None
+        del out
+        if it >= 2:
+            api.append(a.elapsed_time(b))
+            ker.append(sum(s.elapsed_time(e) for _, s, e, _ in prof) if prof else float('nan'))
+    return statistics.median(api), statistics.median(ker)
+
+
+def row(results, cfg, name, nbytes, tokens, fn, reps, aten=None):
+    api_ms, ker_ms = timed(fn, reps)
+    r = {'cfg': cfg, 'op': name, 'api_ms': api_ms, 'kernel_ms': ker_ms, 'alg_GB': nbytes / 1e9,
+         'api_GBs': nbytes / api_ms / 1e6, 'kernel_GBs': nbytes / ker_ms / 1e6 if ker_ms == ker_ms else None,
+         'Mtok_s': tokens / api_ms / 1e3}
+    r['kernel_frac_of_measured_peak'] = r['kernel_GBs'] / PEAK if r['kernel_GBs'] else None
+    r['api_frac_of_measured_peak'] = r['api_GBs'] / PEAK
+    if aten is not None:
+        aten_ms, _ = timed(aten, max(3, reps // 2), clear=False)
+        r['aten_payload_ms'] = aten_ms
+        r['speedup_vs_aten_payload'] = aten_ms / api_ms
+    results.append(r)
+    k = f"{r['kernel_GBs']:7.0f}" if r['kernel_GBs'] else '      -'
+    extra = f"  aten {r['aten_payload_ms']:8.3f} ms (x{r['speedup_vs_aten_payload']:.1f})" if aten is not None else ''
+    print(f"cfg{cfg} {name:28s} api {api_ms:8.3f} ms {r['api_GBs']:7.0f} GB/s | kernel {k} GB/s "
+          f"({(r['kernel_frac_of_measured_peak'] or 0) * 100:5.1f}% of {PEAK:.0f}) | {r['Mtok_s']:9.1f} Mtok/s{extra}",
+          flush=True)
+
+
+def cfg2(results, reps):
+    g = torch.Generator().manual_seed(0)
+    lens = torch.randint(1, 513, (4096,), generator=g)
+    n, b, t, d = int(lens.sum()), 4096, int(lens.max()), 2048
+    data = torch.randn((n, 1024), device='cuda').to(torch.bfloat16)
+    c = rua.C(data=data, token_sizes=lens.cuda())
+    srcs = {'C': c, 'L': c.left(0), 'R': c.right(0), 'P': c.pack()}
+    nd, btd = n * d, b * t * d
+    conv = {'C': lambda z: z.cat(), 'L': lambda z: z.left(0), 'R': lambda z: z.right(0), 'P': lambda z: z.pack()}
+    # the index the reference would gather with, precomputed (payload-only ATen baseline)
+    bp, tp = srcs['P'].ptr()
+    key_cp = (c.offsets()[bp] + tp)
+    for sk in 'CLPR':
+        for dk in 'CLPR':
+            if sk == dk:
+                continue
+            nbytes = (nd + btd + 8 * b) if dk in 'LR' else (2 * nd + 8 * b + (8 * t if 'P' in (sk, dk) else 0))
+            aten = (lambda: torch.index_select(data, 0, key_cp)) if (sk, dk) == ('C', 'P') else None
+            row(results, 2, f'{sk}->{dk}', nbytes, n, lambda s=srcs[sk], f=conv[dk]: f(s), reps, aten)
+    for sk in 'CP':
+        s = srcs[sk]
+        row(results, 2, f'{sk}.rev', 2 * nd, n, lambda s=s: s.rev(), reps)
+        row(results, 2, f'{sk}.roll(1)', 2 * nd, n, lambda s=s: s.roll(1), reps)
+        row(results, 2, f'{sk}.last', 2 * b * d + 8 * b, n, lambda s=s: s.last(), reps)
+    row(results, 2, 'C.head(1)', 2 * b * d, n, lambda: c.head(1), reps)
+    row(results, 2, 'C.bmask', b * t + 8 * b, n, lambda: c.bmask(), reps)
+    row(results, 2, 'C.fmask', b * t * 2 + 8 * b, n, lambda: c.fmask(), reps)
+    for fn in ('sum', 'max', 'logsumexp'):
+        f = getattr(rua, 'segment_' + fn)
+        aten = None
+        if fn in ('sum', 'max'):
+            lc = lens.cuda()
+            aten = lambda fn=fn, lc=lc: torch.segment_reduce(data, fn, lengths=lc, unsafe=True)
+        row(results, 2, f'segment_{fn}', nd + b * d + 8 * b, n, lambda f=f: f(data, c.token_sizes), reps, aten)
+
+
+def cfg3(results, reps):
+    rng = np.random.default_rng(0)
+    sizes = np.minimum(rng.zipf(1.5, 16384), 4096).astype(np.int64)
+    n, s, d = int(sizes.sum()), 16384, 8192
+    print(f'cfg3: B={s}, Zipf(a=1.5) clipped to 4096, N={n}, hidden 4096 bf16, payload {n * d / 1e9:.2f} GB', flush=True)
+    data = torch.randn((n, 4096), device='cuda', dtype=torch.bfloat16)
+    sz = torch.from_numpy(sizes).cuda()
+    nd = n * d
+    for fn in ('sum', 'mean', 'max', 'min', 'logsumexp', 'prod'):
+        f = getattr(rua, 'segment_' + fn)
+        aten = (lambda fn=fn: torch.segment_reduce(data, fn, lengths=sz, unsafe=True)) if fn in ('sum', 'max') else None
+        row(results, 3, f'segment_{fn}', nd + s * d + 8 * s, n, lambda f=f: f(data, sz), reps, aten)
+    c = rua.C(data=data, token_sizes=sz)
+    p = c.pack()
+    for name, z in (('C', c), ('P', p)):
+        row(results, 3, f'{name}.head(1)', 2 * s * d, n, lambda z=z: z.head(1), reps)
+        row(results, 3, f'{name}.last', 2 * s * d + 8 * s, n, lambda z=z: z.last(), reps)
+        row(results, 3, f'{name}.roll(1)', 2 * nd, n, lambda z=z: z.roll(1), reps)
+        row(results, 3, f'{name}.rev', 2 * nd, n, lambda z=z: z.rev(), reps)
+    row(results, 3, 'C->P', 2 * nd, n, lambda: c.pack(), reps)
+    row(results, 3, 'P->C', 2 * nd, n, lambda: p.cat(), reps)
+
+
+def cfg5(results, reps):
+    g = torch.Generator().manual_seed(0)
+    lens = torch.randint(1, 65, (1_000_000,), generator=g)
+    n, b, t = int(lens.sum()), 1_000_000, 64
+    data = torch.arange(n, dtype=torch.long, device='cuda')
+    lc = lens.cuda()
+    c = rua.C(data=data, token_sizes=lc)
+    left = c.left(0)
+    p = c.pack()
+    row(results, 5, 'C.offsets', 16 * b, n, lambda: c.offsets(), reps,
+        aten=lambda: torch.cumsum(lc, 0).roll(1))
+    row(results, 5, 'C.bmask', b * t + 8 * b, n, lambda: c.bmask(), reps)
+    row(results, 5, 'C.mask(long)', b * t * 8 + 8 * b, n, lambda: c.mask(-1, 2, torch.long), reps)
+    row(results, 5, 'C.ptr', 16 * n + 8 * b, n, lambda: c.ptr(), reps,
+        aten=lambda: torch.repeat_interleave(lc, output_size=n))
+    row(results, 5, 'P.ptr', 16 * n + 8 * b, n, lambda: p.ptr(), reps)
+    row(results, 5, 'L.idx', 8 * n + 8 * b, n, lambda: left.idx(), reps)
+    row(results, 5, 'pack_view (sort+bs)', 8 * b * 3 + 8 * t, n, lambda: c.pack_view(), reps,
+        aten=lambda: torch.sort(lc, descending=True, stable=True))
+    row(results, 5, 'P lengths (cat_view)', 16 * b + 8 * t, n, lambda: p.cat_view(), reps)
+    row(results, 5, 'C->P (8 B rows)', 16 * n + 8 * (b + t), n, lambda: c.pack(), reps)
+    row(results, 5, 'C->L (8 B rows)', 8 * n + 8 * b * t + 8 * b, n, lambda: c.left(0), reps)
+    row(results, 5, 'P->C (8 B rows)', 16 * n + 8 * (b + t), n, lambda: p.cat(), reps)
+    row(results, 5, 'L->C (8 B rows)', 16 * n + 8 * b, n, lambda: left.cat(), reps)
+    row(results, 5, 'C.rev (8 B rows)', 16 * n, n, lambda: c.rev(), reps)
+    fdata = torch.randn(n, device='cuda')
+    row(results, 5, 'segment_sum (H=1 fp32)', 4 * n + 4 * b + 8 * b, n, lambda: rua.segment_sum(fdata, lc), reps,
+        aten=lambda: torch.segment_reduce(fdata, 'sum', lengths=lc, unsafe=True))
+    row(results, 5, 'segment_max (H=1 fp32)', 4 * n + 4 * b + 8 * b, n, lambda: rua.segment_max(fdata, lc), reps)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--cfg', type=int, nargs='+', default=[2, 3, 5])
+    ap.add_argument('--reps', type=int, default=10)
+    ap.add_argument('--out', default=None)
+    args = ap.parse_args()
+    results = []
+    for k in args.cfg:
+        {2: cfg2, 3: cfg3, 5: cfg5}[k](results, args.reps)
+        torch.cuda.empty_cache()
+    if args.out:
+        os.makedirs(os.path.dirname(os.path.abspath(args.out)), exist_ok=True)
+        json.dump({'peak_GBs': PEAK, 'gpu': torch.cuda.get_device_name(0), 'rows': results}, open(args.out, 'w'), indent=1)
+
+
+if __name__ == '__main__':
+    main()

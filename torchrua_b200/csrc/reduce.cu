@@ -122,7 +122,7 @@ __device__ __forceinline__ void load_partial(const A* base, int64_t H, int64_t c
 // main kernel
 // ---------------------------------------------------------------------------------------------
 template <typename T, int V, int OP>
-__global__ void __launch_bounds__(kRedThreads)
+__global__ void __launch_bounds__(kRedThreads, Store<T>::kMinBlocks)
 segreduce_kernel(const T* __restrict__ data, const int64_t* __restrict__ off, int64_t N, int64_t S, int64_t H,
                  int R, T* __restrict__ out, typename Store<T>::Acc* __restrict__ head,
                  typename Store<T>::Acc* __restrict__ tail, RedHeader* hdr) {
@@ -144,6 +144,7 @@ segreduce_kernel(const T* __restrict__ data, const int64_t* __restrict__ off, in
   State<A, V, OP> st;
   st.reset();
   A ext = OP == RUA_MIN ? -inf_of<A>() : inf_of<A>();
+  uint32_t ext2[4] = {Pk<T>::kPosInf, Pk<T>::kPosInf, Pk<T>::kPosInf, Pk<T>::kPosInf};  // packed running min
   bool saw_nan = false;
 
   const T* colp = data + col;
@@ -154,43 +155,66 @@ segreduce_kernel(const T* __restrict__ data, const int64_t* __restrict__ off, in
       for (int k = 0; k < kRedUnroll; ++k)
         if (r + k < row1) load_raw<T, V>(colp + (r + k) * H, raw[k]);
     }
-#pragma unroll
-    for (int k = 0; k < kRedUnroll; ++k) {
-      const int64_t row = r + k;
-      if (row < row1) {
-        if (active) {
-          A x[V];
-          unpack_raw<T, V>(raw[k], x);
-          st.template add<kFast>(x);
-          if (OpInfo<OP>::kNeedsExt) {
-#pragma unroll
-            for (int v = 0; v < V; ++v) ext = OP == RUA_MIN ? max_num(ext, x[v]) : min_num(ext, x[v]);
-          }
-        }
-        pending = true;
-        if (row + 1 == seg_end) {  // uniform across the CTA
-          if (active) {
-            if (open) {
-              store_partial<A, V, OP>(head + chunk * P * H, H, col, st);
-            } else {
-              A o[V];
-              st.finalize(seg_end - seg_beg, o);
-              if (OpInfo<OP>::kNeedsExt) saw_nan |= st.any_nan_out(o);
-              store_vec<T, V>(out + s * H + col, o);
-            }
-          }
-          st.reset();
-          open = false;
-          pending = false;
-          do {  // next non-empty segment
-            ++s;
-            seg_beg = seg_end;
-            seg_end = s < S ? __ldg(off + s + 1) : (int64_t)0x7fffffffffffffffll;
-          } while (s < S && seg_end == seg_beg);
+    // the current segment ends after row `seg_end - 1`: store it and move to the next non-empty one
+    auto finish_segment = [&]() {
+      if (active) {
+        if (open) {
+          store_partial<A, V, OP>(head + chunk * P * H, H, col, st);
+        } else {
+          A o[V];
+          st.finalize(seg_end - seg_beg, o);
+          if (OpInfo<OP>::kNeedsExt) saw_nan |= st.any_nan_out(o);
+          store_vec<T, V>(out + s * H + col, o);
         }
       }
+      st.reset();
+      open = false;
+      pending = false;
+      do {
+        ++s;
+        seg_beg = seg_end;
+        seg_end = s < S ? __ldg(off + s + 1) : (int64_t)0x7fffffffffffffffll;
+      } while (s < S && seg_end == seg_beg);
+    };
+
+    // Walk the batch run by run: rows [k, e) of the batch belong to the current segment.  Register
+    // arrays need static indices, so the per-row code is an unrolled, range-predicated sweep; the
+    // (large) segment-finalising code appears once per kernel instead of once per unrolled row.
+    const int nrows = (int)(row1 - r < kRedUnroll ? row1 - r : kRedUnroll);
+    int k = 0;
+    while (k < nrows) {
+      const int64_t left_in_seg = seg_end - r;
+      const int e = (int)(left_in_seg < nrows ? left_in_seg : nrows);
+      bool done = false;
+      if constexpr (OpInfo<OP>::kIsLse) {
+        if (k == 0 && e == kRedUnroll) {
+          // fast path (uniform): all 8 rows belong to the current segment.  Batch max first, one rescale
+          // of the running sum, then exactly one FFMA + EX2 + FADD per element; for 16-bit storage the
+          // max and the global-extreme tracking run on packed pairs (HMNMX2), halving their issue cost.
+          if (active) lse_batch<T, V, kRedUnroll>(raw, st.a, st.s, ext, ext2);
+          done = true;
+        }
+      }
+      if (!done && active) {
+#pragma unroll
+        for (int kk = 0; kk < kRedUnroll; ++kk) {
+          if (kk >= k && kk < e) {
+            A x[V];
+            unpack_raw<T, V>(raw[kk], x);
+            st.template add<kFast>(x);
+            if (OpInfo<OP>::kNeedsExt) {
+#pragma unroll
+              for (int v = 0; v < V; ++v) ext = OP == RUA_MIN ? max_num(ext, x[v]) : min_num(ext, x[v]);
+            }
+          }
+        }
+      }
+      pending = true;
+      k = e;
+      if (r + e == seg_end) finish_segment();  // uniform across the CTA
     }
   }
+  if (OpInfo<OP>::kIsLse) ext = min_num(ext, packed_min_to_acc<T, V>(ext2));
   if (pending && active) {
     // the segment continues in the next chunk: whole-chunk pieces go to `head`, suffix pieces to `tail`
     store_partial<A, V, OP>((open ? head : tail) + chunk * P * H, H, col, st);

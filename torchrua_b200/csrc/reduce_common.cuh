@@ -19,6 +19,7 @@ template <typename T> struct Store;
 template <> struct Store<float> {
   using Acc = float;
   static constexpr int kVec = 4;
+  static constexpr int kMinBlocks = 6;  // CTAs of 128 threads per SM the main kernel is compiled for (<= 85 regs)
   __device__ static void unpack(const uint4& r, Acc* x) {
     x[0] = __uint_as_float(r.x); x[1] = __uint_as_float(r.y); x[2] = __uint_as_float(r.z); x[3] = __uint_as_float(r.w);
   }
@@ -31,6 +32,7 @@ template <> struct Store<float> {
 template <> struct Store<double> {
   using Acc = double;
   static constexpr int kVec = 2;
+  static constexpr int kMinBlocks = 4;
   __device__ static void unpack(const uint4& r, Acc* x) {
     x[0] = __hiloint2double((int)r.y, (int)r.x);
     x[1] = __hiloint2double((int)r.w, (int)r.z);
@@ -45,6 +47,7 @@ template <> struct Store<double> {
 template <> struct Store<__half> {
   using Acc = float;
   static constexpr int kVec = 8;
+  static constexpr int kMinBlocks = 4;  // half2 -> float2 unpacking needs more registers than the bf16 shift
   __device__ static void unpack(const uint4& r, Acc* x) {
     const uint32_t w[4] = {r.x, r.y, r.z, r.w};
 #pragma unroll
@@ -68,6 +71,7 @@ template <> struct Store<__half> {
 template <> struct Store<__nv_bfloat16> {
   using Acc = float;
   static constexpr int kVec = 8;
+  static constexpr int kMinBlocks = 6;
   __device__ static void unpack(const uint4& r, Acc* x) {
     const uint32_t w[4] = {r.x, r.y, r.z, r.w};
 #pragma unroll
@@ -156,6 +160,143 @@ template <typename T, int V>
 __device__ __forceinline__ void store_vec(T* p, const typename Store<T>::Acc* x) {
   if constexpr (V == 1) *p = Store<T>::from_acc(x[0]);
   else *reinterpret_cast<uint4*>(p) = Store<T>::pack(x);
+}
+
+// ---------------------------------------------------------------------------------------------
+// packed 16-bit pairs: max / min are exact in the storage format, so they can run two-at-a-time
+// (HMNMX2) on the raw words without unpacking to fp32
+// ---------------------------------------------------------------------------------------------
+template <typename T> struct Pk {
+  static constexpr bool kHas = false;
+  static constexpr uint32_t kPosInf = 0u;
+};
+template <> struct Pk<__nv_bfloat16> {
+  static constexpr bool kHas = true;
+  static constexpr uint32_t kPosInf = 0x7F807F80u;
+  __device__ static __forceinline__ uint32_t max_nan(uint32_t a, uint32_t b) {
+    __nv_bfloat162 r = __hmax2_nan(*reinterpret_cast<__nv_bfloat162*>(&a), *reinterpret_cast<__nv_bfloat162*>(&b));
+    return *reinterpret_cast<uint32_t*>(&r);
+  }
+  __device__ static __forceinline__ uint32_t min_num(uint32_t a, uint32_t b) {
+    __nv_bfloat162 r = __hmin2(*reinterpret_cast<__nv_bfloat162*>(&a), *reinterpret_cast<__nv_bfloat162*>(&b));
+    return *reinterpret_cast<uint32_t*>(&r);
+  }
+  __device__ static __forceinline__ void unpack(uint32_t w, float& lo, float& hi) {
+    lo = __uint_as_float(w << 16);
+    hi = __uint_as_float(w & 0xffff0000u);
+  }
+};
+template <> struct Pk<__half> {
+  static constexpr bool kHas = true;
+  static constexpr uint32_t kPosInf = 0x7C007C00u;
+  __device__ static __forceinline__ uint32_t max_nan(uint32_t a, uint32_t b) {
+    __half2 r = __hmax2_nan(*reinterpret_cast<__half2*>(&a), *reinterpret_cast<__half2*>(&b));
+    return *reinterpret_cast<uint32_t*>(&r);
+  }
+  __device__ static __forceinline__ uint32_t min_num(uint32_t a, uint32_t b) {
+    __half2 r = __hmin2(*reinterpret_cast<__half2*>(&a), *reinterpret_cast<__half2*>(&b));
+    return *reinterpret_cast<uint32_t*>(&r);
+  }
+  __device__ static __forceinline__ void unpack(uint32_t w, float& lo, float& hi) {
+    float2 f = __half22float2(*reinterpret_cast<__half2*>(&w));
+    lo = f.x;
+    hi = f.y;
+  }
+};
+
+__device__ __forceinline__ uint32_t word_of(const uint4& w, int j) {
+  return j == 0 ? w.x : (j == 1 ? w.y : (j == 2 ? w.z : w.w));
+}
+
+template <typename T, int V>
+__device__ __forceinline__ typename Store<T>::Acc packed_min_to_acc(const uint32_t* ext2) {
+  using A = typename Store<T>::Acc;
+  A m = inf_of<A>();
+  if constexpr (Pk<T>::kHas && V == 8) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      float lo, hi;
+      Pk<T>::unpack(ext2[j], lo, hi);
+      m = min_num(m, min_num(lo, hi));
+    }
+  }
+  return m;
+}
+
+__device__ __forceinline__ float ex2_approx(float x) {
+  float r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+
+// logsumexp over kRows rows that all belong to the current segment: a[] = running max, s[] = running
+// sum of exp(x - a).  One EX2 per element (plus one per column for the rescale).
+template <typename T, int V, int kRows>
+__device__ __forceinline__ void lse_batch(const Raw<T, V>* raw, typename Store<T>::Acc* a, typename Store<T>::Acc* s,
+                                          typename Store<T>::Acc& ext, uint32_t* ext2) {
+  using A = typename Store<T>::Acc;
+  A bm[V];
+  if constexpr (Pk<T>::kHas && V == 8) {
+    uint32_t m2[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) m2[j] = word_of(raw[0].r, j);
+#pragma unroll
+    for (int k = 0; k < kRows; ++k) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        uint32_t w = word_of(raw[k].r, j);
+        if (k > 0) m2[j] = Pk<T>::max_nan(m2[j], w);
+        ext2[j] = Pk<T>::min_num(ext2[j], w);
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) Pk<T>::unpack(m2[j], bm[2 * j], bm[2 * j + 1]);
+  } else {
+#pragma unroll
+    for (int v = 0; v < V; ++v) bm[v] = -inf_of<A>();
+#pragma unroll
+    for (int k = 0; k < kRows; ++k) {
+      A x[V];
+      unpack_raw<T, V>(raw[k], x);
+#pragma unroll
+      for (int v = 0; v < V; ++v) {
+        bm[v] = max_nan(bm[v], x[v]);
+        ext = min_num(ext, x[v]);
+      }
+    }
+  }
+  if constexpr (sizeof(A) == 4) {
+    constexpr float kLog2e = 1.4426950408889634f;
+    float mb[V];
+#pragma unroll
+    for (int v = 0; v < V; ++v) {
+      float m_new = max_nan(a[v], bm[v]);
+      s[v] = s[v] == 0.f ? 0.f : s[v] * ex2_approx((a[v] - m_new) * kLog2e);
+      a[v] = m_new;
+      mb[v] = m_new * kLog2e;
+    }
+#pragma unroll
+    for (int k = 0; k < kRows; ++k) {
+      A x[V];
+      unpack_raw<T, V>(raw[k], x);
+#pragma unroll
+      for (int v = 0; v < V; ++v) s[v] += ex2_approx(fmaf(x[v], kLog2e, -mb[v]));
+    }
+  } else {
+#pragma unroll
+    for (int v = 0; v < V; ++v) {
+      A m_new = max_nan(a[v], bm[v]);
+      s[v] = s[v] == A(0) ? A(0) : s[v] * exp(a[v] - m_new);
+      a[v] = m_new;
+    }
+#pragma unroll
+    for (int k = 0; k < kRows; ++k) {
+      A x[V];
+      unpack_raw<T, V>(raw[k], x);
+#pragma unroll
+      for (int v = 0; v < V; ++v) s[v] += exp(x[v] - a[v]);
+    }
+  }
 }
 
 

@@ -131,6 +131,15 @@ int rua_batch_sizes(const int64_t* len, const int64_t* sorted, int64_t B, int64_
 int rua_lengths_from_pack(const int64_t* bs, const int64_t* unsorted, int64_t B, int64_t T,
                           int64_t* len, rua_stream_t stream);
 
+/* One-launch metadata for B <= rua_meta_fused_max_batch() sequences (a single CTA; bitonic sort in
+ * shared memory): off[B+1]; hostbuf[0] = N, hostbuf[1] = T; and, when `sorted` != NULL, the stable
+ * descending permutation + inverse, hostbuf[2 + t] = batch_sizes[t] and poff[t] for t < min(T, cap),
+ * poff[min(T,cap)] = N (or -1 if T > cap: re-run with a larger cap).  hostbuf has 2 + cap entries so
+ * the caller can fetch N, T and batch_sizes with ONE device->host copy (pack_view, core/view.py:47-58). */
+int64_t rua_meta_fused_max_batch(void);
+int rua_meta_fused(const int64_t* len, int64_t B, int64_t* off, int64_t* sorted, int64_t* unsorted,
+                   int64_t* hostbuf, int64_t* poff, int64_t cap, rua_stream_t stream);
+
 /* ------------------------------------------------------------------------------------------- */
 /* K1/K2  ragged row map: the 12 layout conversions, the selects and their backward passes       */
 /* replaces to_cat / cat_pack_to_left / right_to_left / to_pack / cat_pack_to_right /            */

@@ -46,7 +46,7 @@ def test_host_only_entry_points(lib):
     assert lib.rua_error_string(0) == b'ok'
     assert lib.rua_error_string(-2) == b'workspace too small'
     assert lib.rua_scan_workspace_bytes(1) >= 8
-    assert lib.rua_scan_workspace_bytes(1 << 20) >= (1 << 20) // 2048 * 8
+    assert lib.rua_scan_workspace_bytes(1 << 20) >= (1 << 20) // 4096 * 8
     assert lib.rua_sort_workspace_bytes(1 << 20) >= 4 * 4 * (1 << 20)
     # argument validation happens before any CUDA call: safe without a GPU
     assert lib.rua_scan_lengths(None, -1, 0, None, None, None, 0, None) == -1

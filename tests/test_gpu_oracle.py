@@ -134,6 +134,23 @@ def test_selects_masks_indices_vs_oracle(rua, name, lens, feat, dtype):
                 assert_seq_equal(s.trunc((a, b_)), ora.trunc(o, (a, b_)), f'{name}: trunc({a},{b_}) {sk}')
 
 
+@pytest.mark.parametrize('b,hi', [(1, 5), (2, 3), (31, 9), (33, 9), (1000, 300), (4096, 512), (8192, 70),
+                                  (8193, 70), (64, 70000), (300, 5000)])
+def test_pack_metadata_paths(rua, b, hi):
+    """one-CTA fused metadata kernel (B <= 8192; 1-3 radix passes; T above the speculative cap) and the
+    general multi-kernel path (B > 8192) against the oracle's stable descending sort."""
+    rng = np.random.default_rng(b * 7 + hi)
+    lens = rng.integers(0 if b > 2 else 1, hi + 1, b).astype(np.int64)
+    lens[rng.integers(0, b)] = hi          # make sure T == hi
+    c = rua.C(data=torch.arange(int(lens.sum()), dtype=torch.int32).cuda(), token_sizes=torch.from_numpy(lens).cuda())
+    p = c.pack()
+    bs, srt, uns = ora.pack_meta(lens)
+    assert same(host(p.batch_sizes), bs) and same(host(p.sorted_indices), srt) and same(host(p.unsorted_indices), uns)
+    assert same(host(p.data), ora.to_pack(ora.Cat(np.arange(int(lens.sum()), dtype=np.int32), lens)).data)
+    assert same(host(p.cat().data), np.arange(int(lens.sum()), dtype=np.int32))
+    assert same(host(c.offsets()), ora.offsets(ora.Cat(host(c.data), lens)))
+
+
 REDUCE_CASES = [
     # name, sizes, feature shape, dtype
     ('short', lambda r: r.integers(1, 9, 200), (12,), torch.float32),

@@ -42,6 +42,9 @@ SIGNATURES = {
     'rua_invert_permutation': (c_int32, [c_void_p, c_int64, c_void_p, c_void_p]),
     'rua_batch_sizes': (c_int32, [c_void_p, c_void_p, c_int64, c_int64, c_void_p, c_void_p]),
     'rua_lengths_from_pack': (c_int32, [c_void_p, c_void_p, c_int64, c_int64, c_void_p, c_void_p]),
+    'rua_meta_fused_max_batch': (c_int64, []),
+    'rua_meta_fused': (c_int32, [c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64,
+                                 c_void_p]),
     'rua_row_map': (c_int32, [c_void_p, c_void_p, c_int64, POINTER(Ragged), POINTER(Side), POINTER(Side),
                               c_int32, c_int64, c_int32, c_char_p, c_int32, c_void_p]),
     'rua_gather_rows': (c_int32, [c_void_p, c_int64, c_void_p, c_int64, c_int64, c_void_p, c_void_p]),

@@ -41,6 +41,46 @@ def _stream() -> int:
     return torch.cuda.current_stream().cuda_stream
 
 
+FUSED_CAP = 4096   # speculative number of batch_sizes entries fetched together with (N, T)
+
+
+class _NoGuard:
+    def __enter__(self):
+        return None
+
+    def __exit__(self, *exc):
+        return False
+
+
+_NO_GUARD = _NoGuard()
+
+
+def _on(device: torch.device):
+    """device guard that costs nothing in the common one-process-per-GPU case (torch.cuda.device() is
+    ~10 us of Python per use; these kernels run for 5 us)."""
+    idx = device.index
+    if idx is None or idx == torch.cuda.current_device():
+        return _NO_GUARD
+    return torch.cuda.device(device)
+
+
+def fetch(dev_tensor: Tensor) -> Tensor:
+    """small device -> host read through pinned memory, ordered on the current stream (no device-wide
+    sync, no pageable staging copy)."""
+    host = torch.empty(dev_tensor.shape, dtype=dev_tensor.dtype, pin_memory=True)
+    with _on(dev_tensor.device):
+        host.copy_(dev_tensor, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+    return host
+
+
+def upload(host_tensor: Tensor, device: torch.device) -> Tensor:
+    """small host -> device write through pinned memory (asynchronous, stream-ordered)."""
+    pinned = torch.empty(host_tensor.shape, dtype=host_tensor.dtype, pin_memory=True)
+    pinned.copy_(host_tensor)
+    return pinned.to(device, non_blocking=True)
+
+
 # optional per-launch timing (bench.py sets PROFILE = [] to collect (name, start, end, algorithmic_bytes);
 # events are recorded on the launching stream right around the kernel launch)
 PROFILE = None
@@ -71,10 +111,24 @@ def _i64(t: Tensor) -> Tensor:
     return t.contiguous()
 
 
+_SCALAR_BYTES = {}
+
+
 def scalar_bytes(value, dtype: torch.dtype) -> bytes:
-    """the in-memory image of ``value`` cast to ``dtype`` (fill / zero / one patterns)."""
-    t = torch.tensor([value], dtype=dtype)
-    return bytes(t.view(torch.uint8).tolist())
+    """the in-memory image of ``value`` cast to ``dtype`` (fill / zero / one patterns); memoised, since
+    building a one-element tensor costs more host time than launching the kernel that uses it."""
+    key = (type(value), value, dtype)
+    try:
+        return _SCALAR_BYTES[key]
+    except (KeyError, TypeError):
+        pass
+    if isinstance(value, Tensor):
+        value = value.item()
+        key = (type(value), value, dtype)
+    out = bytes(torch.tensor([value], dtype=dtype).view(torch.uint8).tolist())
+    if len(_SCALAR_BYTES) < 1024:
+        _SCALAR_BYTES[key] = out
+    return out
 
 
 # ------------------------------------------------------------------------------------------------
@@ -89,14 +143,14 @@ def scan(sizes: Tensor, clamp_max: int = INT64_MAX) -> Tuple[Tensor, Tensor]:
     sizes = _i64(sizes)
     require_cuda(sizes)
     n = sizes.numel()
-    with torch.cuda.device(sizes.device):
-        off = torch.empty(n + 1, dtype=torch.long, device=sizes.device)
-        stats = torch.empty(2, dtype=torch.long, device=sizes.device)
-        nbytes = lib.rua_scan_workspace_bytes(n)
-        ws = torch.empty(nbytes, dtype=torch.uint8, device=sizes.device)
-        _lib.check(lib.rua_scan_lengths(sizes.data_ptr(), n, clamp_max, off.data_ptr(), stats.data_ptr(),
-                                        ws.data_ptr(), nbytes, _stream()), 'rua_scan_lengths')
-    return off, stats
+    tiles = max((n + 2047) // 2048, 1)      # == rua_scan_workspace_bytes(n) / 8
+    with _on(sizes.device):
+        # one allocation: [off (n+1) | stats (2) | tile status words (tiles)]
+        buf = torch.empty(n + 3 + tiles, dtype=torch.long, device=sizes.device)
+        base = buf.data_ptr()
+        _lib.check(lib.rua_scan_lengths(sizes.data_ptr(), n, clamp_max, base, base + 8 * (n + 1),
+                                        base + 8 * (n + 3), 8 * tiles, _stream()), 'rua_scan_lengths')
+    return buf[:n + 1], buf[n + 1:n + 3]
 
 
 @dataclass
@@ -119,7 +173,8 @@ class Ragged:
     _keep: list = field(default_factory=list)
 
     def _sync_stats(self):
-        n, t = self.stats.tolist()   # the one inherent D2H: output shapes depend on device data
+        # the one inherent D2H: output shapes depend on device data (16 bytes, pinned, stream-ordered)
+        n, t = fetch(self.stats).tolist()
         self._N, self._T = int(n), int(t)
 
     @property
@@ -145,8 +200,10 @@ class Ragged:
             return self
         lib = _lib.load()
         dev = self.device
+        if self.sorted is None and 0 < self.B <= lib.rua_meta_fused_max_batch():
+            return self._ensure_pack_fused()
         T = self.T
-        with torch.cuda.device(dev):
+        with _on(dev):
             if self.sorted is None:
                 self.sorted = torch.empty(self.B, dtype=torch.long, device=dev)
                 self.unsorted = torch.empty(self.B, dtype=torch.long, device=dev)
@@ -160,7 +217,36 @@ class Ragged:
                                            self.bs_dev.data_ptr(), _stream()), 'rua_batch_sizes')
         self.poff, _ = scan(self.bs_dev)
         self.Tp = T
-        self.bs_cpu = self.bs_dev.cpu()
+        self.bs_cpu = fetch(self.bs_dev).clone()
+        _cache_put(self.unsorted, 'pack', self)
+        return self
+
+    def _ensure_pack_fused(self) -> 'Ragged':
+        """B <= 16384: ONE kernel (scan + bitonic sort + batch_sizes + their prefix sums) and ONE
+        device->host copy of [N, T, batch_sizes]."""
+        lib = _lib.load()
+        dev = self.device
+        cap = self._T if self._T is not None else FUSED_CAP
+        while True:
+            with _on(dev):
+                self.sorted = torch.empty(self.B, dtype=torch.long, device=dev)
+                self.unsorted = torch.empty(self.B, dtype=torch.long, device=dev)
+                hostbuf = torch.empty(2 + cap, dtype=torch.long, device=dev)
+                poff = torch.empty(cap + 1, dtype=torch.long, device=dev)
+                _lib.check(lib.rua_meta_fused(self.len.data_ptr(), self.B, self.off.data_ptr(), self.sorted.data_ptr(),
+                                              self.unsorted.data_ptr(), hostbuf.data_ptr(), poff.data_ptr(), cap,
+                                              _stream()), 'rua_meta_fused')
+            host = fetch(hostbuf)
+            n, t = int(host[0]), int(host[1])
+            if t <= cap:
+                break
+            cap = t   # a sequence longer than the speculative cap: one more round trip, exact this time
+        self._N, self._T, self.Tp = n, t, t
+        self.bs_cpu = host[2:2 + t].clone()
+        self.bs_dev = hostbuf[2:2 + t]
+        self.poff = poff[:t + 1]
+        self._keep += [hostbuf, poff]
+        _cache_put(self.unsorted, 'pack', self)
         return self
 
 
@@ -185,16 +271,29 @@ def _cache_put(key_tensor: Tensor, tag: str, value):
     _CACHE[(id(key_tensor), tag)] = (weakref.ref(key_tensor), key_tensor._version, value)
 
 
-def ragged_from_lengths(token_sizes: Tensor) -> Ragged:
-    """lengths -> Ragged (one scan kernel; cached per lengths tensor object + version)."""
+FUSED_MAX_B = 8192   # == rua_meta_fused_max_batch()
+
+
+def ragged_from_lengths(token_sizes: Tensor, want_pack: bool = False) -> Ragged:
+    """lengths -> Ragged, cached per lengths tensor object + version.  One scan kernel; or, when the
+    pack side is wanted and the batch is small enough, one fused kernel that produces everything."""
     hit = _cache_get(token_sizes, 'len')
     if hit is not None:
-        return hit
+        return hit.ensure_pack() if want_pack else hit
     dev = require_cuda(token_sizes)
     lens = _i64(token_sizes)
-    off, stats = scan(lens)
-    rg = Ragged(device=dev, B=lens.numel(), len=lens, off=off, stats=stats)
+    b = lens.numel()
+    if want_pack and 0 < b <= FUSED_MAX_B:
+        rg = Ragged(device=dev, B=b, len=lens, off=torch.empty(b + 1, dtype=torch.long, device=dev))
+        rg._ensure_pack_fused()
+    else:
+        off, stats = scan(lens)
+        rg = Ragged(device=dev, B=b, len=lens, off=off, stats=stats)
+        if want_pack:
+            rg.ensure_pack()
     _cache_put(token_sizes, 'len', rg)
+    if lens is not token_sizes:
+        _cache_put(lens, 'len', rg)   # rg.len is what P -> C/L/R conversions hand out as token_sizes
     return rg
 
 
@@ -214,13 +313,13 @@ def ragged_from_pack(batch_sizes: Tensor, sorted_indices: Optional[Tensor], unso
     Tp = bs_cpu.numel()
     # B counts every sequence, including empty ones that never show up in batch_sizes
     B = unsorted_indices.numel() if unsorted_indices is not None else (int(bs_cpu[0]) if Tp > 0 else 0)
-    with torch.cuda.device(device):
+    with _on(device):
         # one H2D for [batch_sizes | poff]
         host = torch.empty(2 * Tp + 1, dtype=torch.long)
         host[:Tp] = bs_cpu
         host[Tp] = 0
         torch.cumsum(bs_cpu, dim=0, out=host[Tp + 1:])
-        devbuf = host.to(device, non_blocking=False)
+        devbuf = upload(host, device)
         bs_dev, poff = devbuf[:Tp], devbuf[Tp:]
         if unsorted_indices is None:   # enforce_sorted=True packs carry no permutation: identity
             unsorted = torch.arange(B, dtype=torch.long, device=device)
@@ -237,6 +336,7 @@ def ragged_from_pack(batch_sizes: Tensor, sorted_indices: Optional[Tensor], unso
                 sorted=srt, unsorted=unsorted, bs_dev=bs_dev, poff=poff, bs_cpu=batch_sizes, Tp=Tp)
     rg._keep.append(devbuf)
     _cache_put(key, 'pack', rg)
+    _cache_put(lens, 'len', rg)   # token_sizes handed out by P -> C/L/R conversions resolve to this entry
     return rg
 
 
@@ -249,7 +349,7 @@ def with_injected_pack(rg: Ragged, sorted_indices: Tensor) -> Ragged:
     new = Ragged(device=rg.device, B=rg.B, len=rg.len, off=rg.off, stats=rg.stats, _N=rg._N, _T=rg._T)
     new.sorted = srt
     new.unsorted = torch.empty_like(srt)
-    with torch.cuda.device(rg.device):
+    with _on(rg.device):
         _lib.check(lib.rua_invert_permutation(srt.data_ptr(), rg.B, new.unsorted.data_ptr(), _stream()),
                    'rua_invert_permutation')
     return new.ensure_pack()
@@ -260,7 +360,7 @@ def invert_permutation(perm: Tensor) -> Tensor:
     require_cuda(perm)
     p = _i64(perm)
     out = torch.empty_like(p)
-    with torch.cuda.device(p.device):
+    with _on(p.device):
         _lib.check(lib.rua_invert_permutation(p.data_ptr(), p.numel(), out.data_ptr(), _stream()),
                    'rua_invert_permutation')
     return out
@@ -307,7 +407,7 @@ def _row_map_raw(src: Tensor, spec: MapSpec, fill: bytes, feat: Tuple[int, ...],
         row_bytes *= f
     rg = spec.rg.c_struct()
     s, d = spec.src.c_struct(), spec.dst.c_struct()
-    with torch.cuda.device(device):
+    with _on(device):
         prof = _profile_begin()
         _lib.check(lib.rua_row_map(_ptr(src), out.data_ptr(), row_bytes, ctypes.byref(rg), ctypes.byref(s),
                                    ctypes.byref(d), spec.tmap, spec.tmap_arg, spec.pad_mode, fill, len(fill),
@@ -353,6 +453,9 @@ def row_map(src_flat: Tensor, spec: MapSpec, fill_value=0) -> Tensor:
     """src_flat: (rows_src, *feat) contiguous flattened storage of the source layout."""
     require_cuda(src_flat)
     fill = scalar_bytes(fill_value, src_flat.dtype)
+    if not (src_flat.requires_grad and torch.is_grad_enabled()):   # no graph to record: skip autograd.Function
+        flat = src_flat if src_flat.is_contiguous() else src_flat.contiguous()
+        return _row_map_raw(flat, spec, fill, tuple(src_flat.shape[1:]), src_flat.dtype, src_flat.device)
     return _RowMap.apply(src_flat, spec, fill)
 
 
@@ -367,7 +470,7 @@ class _GatherRows(torch.autograd.Function):
         out = torch.empty((idx.numel(),) + tuple(flat.shape[1:]), dtype=flat.dtype, device=flat.device)
         if out.numel() > 0:
             row_bytes = flat.element_size() * (flat[0].numel() if flat.shape[0] else 0)
-            with torch.cuda.device(flat.device):
+            with _on(flat.device):
                 _lib.check(lib.rua_gather_rows(flat.data_ptr(), flat.shape[0], idx.data_ptr(), idx.numel(),
                                                row_bytes, out.data_ptr(), _stream()), 'rua_gather_rows')
         return out.view(tuple(index.shape) + tuple(flat.shape[1:]))
@@ -400,7 +503,7 @@ def scatter_rows_(dst: Tensor, index: Tensor, value: Tensor) -> None:
     if val.numel() == 0:
         return
     row_bytes = dst.element_size() * (dst[0].numel())
-    with torch.cuda.device(dst.device):
+    with _on(dst.device):
         _lib.check(lib.rua_scatter_rows(val.data_ptr(), idx.data_ptr(), idx.numel(), row_bytes, dst.data_ptr(),
                                         dst.shape[0], _stream()), 'rua_scatter_rows')
 
@@ -414,9 +517,12 @@ def mask(rg: Ragged, width: int, zero, one, dtype: torch.dtype) -> Tensor:
     if out.numel() == 0:
         return out
     z, o = scalar_bytes(zero, dtype), scalar_bytes(one, dtype)
-    with torch.cuda.device(rg.device):
+    with _on(rg.device):
+        prof = _profile_begin()
         _lib.check(lib.rua_mask(rg.len.data_ptr(), rg.B, width, z, o, out.element_size(), out.data_ptr(),
                                 _stream()), 'rua_mask')
+        if prof is not None:
+            _profile_end(prof, 'mask', out.numel() * out.element_size() + 8 * rg.B)
     return out
 
 
@@ -429,9 +535,13 @@ def emit_ptr(off: Tensor, n: int, relabel: Optional[Tensor] = None, want_which=T
     within = torch.empty(n, dtype=torch.long, device=dev) if want_within else None
     flat = torch.empty(n, dtype=torch.long, device=dev) if flat_stride else None
     if n > 0:
-        with torch.cuda.device(dev):
+        with _on(dev):
+            prof = _profile_begin()
             _lib.check(lib.rua_emit_ptr(off.data_ptr(), S, n, _ptr(relabel), _ptr(which), _ptr(within), _ptr(flat),
                                         flat_stride, int(right_align), _stream()), 'rua_emit_ptr')
+            if prof is not None:
+                outs = int(want_which) + int(want_within) + int(bool(flat_stride))
+                _profile_end(prof, 'emit_ptr', 8 * n * outs + 8 * S)
     return which, within, flat
 
 
@@ -453,7 +563,7 @@ def _reduce_raw(data: Tensor, off: Tensor, S: int, op: int) -> Tensor:
     if out.numel() == 0:
         return out
     dt = _DTYPES[data.dtype]
-    with torch.cuda.device(data.device):
+    with _on(data.device):
         nbytes = lib.rua_segment_reduce_workspace_bytes(N, S, H, dt, op)
         ws = torch.empty(nbytes, dtype=torch.uint8, device=data.device)
         prof = _profile_begin()
@@ -486,7 +596,7 @@ class _SegmentReduce(torch.autograd.Function):
         grad = torch.empty_like(data)
         if grad.numel() > 0:
             dt = _DTYPES[data.dtype]
-            with torch.cuda.device(data.device):
+            with _on(data.device):
                 nbytes = lib.rua_segment_reduce_backward_workspace_bytes(N, ctx.S, H, dt, ctx.op)
                 ws = torch.empty(max(nbytes, 16), dtype=torch.uint8, device=data.device)
                 _lib.check(lib.rua_segment_reduce_backward(g.data_ptr(), out.data_ptr(), data.data_ptr(),
@@ -499,4 +609,6 @@ class _SegmentReduce(torch.autograd.Function):
 def segment_reduce(data: Tensor, segment_sizes: Tensor, op: str) -> Tensor:
     require_cuda(data, segment_sizes)
     rg = ragged_from_lengths(segment_sizes)
+    if not (data.requires_grad and torch.is_grad_enabled()):
+        return _reduce_raw(data if data.is_contiguous() else data.contiguous(), rg.off, rg.B, _OPS[op])
     return _SegmentReduce.apply(data, rg.off, rg.B, _OPS[op])

@@ -68,8 +68,10 @@ R.left = to_left
 def to_pack(self: Z, sorted_indices: Optional[Tensor] = None) -> P:
     """``sorted_indices`` (extension): pack with an externally supplied permutation instead of the
     device sort -- parity mode against the reference's non-stable CPU sort (SURVEY.md 8c hazard 1)."""
-    rg = self._ragged()
-    rg = rg.ensure_pack() if sorted_indices is None else _native.with_injected_pack(rg, sorted_indices)
+    if sorted_indices is None:
+        rg = self._ragged(want_pack=True)   # small batches: one fused metadata kernel, one D2H
+    else:
+        rg = _native.with_injected_pack(self._ragged(), sorted_indices)
     data = _convert(self, rg, SideSpec(PACK, rows=rg.N))
     return P(data=data, batch_sizes=rg.bs_cpu, sorted_indices=rg.sorted, unsorted_indices=rg.unsorted)
 

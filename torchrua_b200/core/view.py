@@ -52,7 +52,7 @@ R.left_view = left_view
 
 
 def pack_view(self: Union[C, L, R], **kwargs) -> P:
-    rg = self._ragged().ensure_pack()
+    rg = self._ragged(want_pack=True)
     return P(
         data=self.data,
         batch_sizes=rg.bs_cpu,

@@ -21,7 +21,7 @@ long long g_launch_count = 0;
 // exclusive scan + max
 // ------------------------------------------------------------------------------------------------
 constexpr int kScanThreads = 256;
-constexpr int kScanItems = 8;
+constexpr int kScanItems = 16;
 constexpr int kScanTile = kScanThreads * kScanItems;  // 2048
 
 __device__ __forceinline__ int64_t warp_incl_scan(int64_t v, int lane) {
@@ -334,10 +334,17 @@ int rua_scan_lengths(const int64_t* sizes, int64_t n, int64_t clamp_max, int64_t
   int multi = tiles > 1;
   if (multi) {
     if (!ws || ws_bytes < rua_scan_workspace_bytes(n)) return RUA_ERR_WORKSPACE;
-    int rc = check_cuda(cudaMemsetAsync(ws, 0, (size_t)tiles * sizeof(unsigned long long), st));
-    if (rc) return rc;
-    rc = check_cuda(cudaMemsetAsync(stats, 0, 2 * sizeof(int64_t), st));
-    if (rc) return rc;
+    int rc;
+    if ((char*)stats + 2 * sizeof(int64_t) == (char*)ws) {
+      // stats sits right in front of the status words (the layout torchrua_b200 uses): one memset
+      rc = check_cuda(cudaMemsetAsync(stats, 0, 2 * sizeof(int64_t) + (size_t)tiles * sizeof(unsigned long long), st));
+      if (rc) return rc;
+    } else {
+      rc = check_cuda(cudaMemsetAsync(ws, 0, (size_t)tiles * sizeof(unsigned long long), st));
+      if (rc) return rc;
+      rc = check_cuda(cudaMemsetAsync(stats, 0, 2 * sizeof(int64_t), st));
+      if (rc) return rc;
+    }
   }
   scan_kernel<<<(unsigned)tiles, kScanThreads, 0, st>>>(sizes, n, clamp_max, off, stats, (unsigned long long*)ws, multi);
   return check_launch();

@@ -73,6 +73,7 @@ def time_cpu(steps: int, warmup: int, budget_s: float):
     """returns (tokens_per_s, ms_per_step, n_seq, n_tokens, threads)"""
     from oracle import c_oracle as co
     co.build()
+    co.use_all_cores()
     n_seq = 512
     while True:
         step, n_tok, _ = cpu_pipeline_factory(n_seq)
@@ -168,7 +169,7 @@ def run_reference(args):
         'e2e': {'value': tps, 'unit': 'tokens/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
         'gpu_launches': 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # --------------------------------------------------------------------------------------------------
@@ -337,12 +338,34 @@ def run_ours(args):
                             'C data, segment_sum and segment_max'},
             'gpu_launches': int(launches), 'clocks': clk,
         }
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 
 
+_JSON_FD = None
+
+
+def protect_stdout():
+    """The contract is ONE JSON line on stdout.  Libraries print there too (NCCL's version banner, for
+    one), so fd 1 is pointed at stderr for the whole run and the JSON line goes to the saved descriptor."""
+    global _JSON_FD
+    sys.stdout.flush()
+    _JSON_FD = os.dup(1)
+    os.dup2(2, 1)
+
+
+def emit(line):
+    data = (json.dumps(line) + '\n').encode()
+    if _JSON_FD is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_JSON_FD, data)
+
+
 def main():
+    protect_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
     ap.add_argument('--steps', type=int, default=20)

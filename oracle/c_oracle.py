@@ -50,6 +50,16 @@ def num_threads() -> int:
     return int(lib().ora_num_threads())
 
 
+def use_all_cores() -> int:
+    """torchrun exports OMP_NUM_THREADS=1; the CPU baseline is meant to use every core it may run on."""
+    try:
+        n = len(os.sched_getaffinity(0))
+    except AttributeError:
+        n = os.cpu_count() or 1
+    lib().ora_set_num_threads(c_int(n))
+    return num_threads()
+
+
 def pack_meta(lens, sorted_in=None):
     lens = _i64(lens)
     B = lens.shape[0]

@@ -211,6 +211,14 @@ void ora_segment_reduce(const void* data, const int64_t* sizes, int64_t S, int64
   free(off);
 }
 
+void ora_set_num_threads(int n) {
+#ifdef _OPENMP
+  if (n > 0) omp_set_num_threads(n);
+#else
+  (void)n;
+#endif
+}
+
 int ora_num_threads(void) {
   int n = 1;
 #ifdef _OPENMP

@@ -1,0 +1,57 @@
+#!/usr/bin/env python
+"""Run ONE op a few times (for `ncu -k regex:...` captures).  python benchmarks/one_op.py <name> [reps]"""
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+import torchrua_b200 as rua  # noqa: E402
+
+name = sys.argv[1]
+reps = int(sys.argv[2]) if len(sys.argv) > 2 else 3
+g = torch.Generator().manual_seed(0)
+
+if name.startswith('cfg5'):
+    lens = torch.randint(1, 65, (1_000_000,), generator=g).cuda()
+    n = int(lens.sum())
+    if name == 'cfg5_flat_sum':
+        x = torch.randn(n, device='cuda')
+        fn = lambda: rua.segment_sum(x, lens)
+    elif name == 'cfg5_flat_max':
+        x = torch.randn(n, device='cuda')
+        fn = lambda: rua.segment_max(x, lens)
+    elif name == 'cfg5_L_to_C':
+        c = rua.C(data=torch.arange(n, device='cuda'), token_sizes=lens)
+        left = c.left(0)
+        fn = lambda: left.cat()
+    elif name == 'cfg5_C_to_L':
+        c = rua.C(data=torch.arange(n, device='cuda'), token_sizes=lens)
+        fn = lambda: c.left(0)
+    elif name == 'cfg5_C_to_P':
+        c = rua.C(data=torch.arange(n, device='cuda'), token_sizes=lens)
+        fn = lambda: c.pack()
+    elif name == 'cfg5_ptr':
+        c = rua.C(data=torch.arange(n, device='cuda'), token_sizes=lens)
+        fn = lambda: c.ptr()
+    elif name == 'cfg5_bmask':
+        c = rua.C(data=torch.arange(n, device='cuda'), token_sizes=lens)
+        fn = lambda: c.bmask()
+    else:
+        raise SystemExit(f'unknown op {name}')
+elif name.startswith('cfg3'):
+    sizes = np.minimum(np.random.default_rng(0).zipf(1.5, 16384), 4096).astype(np.int64)
+    x = torch.randn((int(sizes.sum()), 4096), device='cuda', dtype=torch.bfloat16)
+    sz = torch.from_numpy(sizes).cuda()
+    op = name.split('_', 1)[1]
+    fn = lambda: getattr(rua, 'segment_' + op)(x, sz)
+else:
+    raise SystemExit(f'unknown op {name}')
+
+for _ in range(reps):
+    out = fn()
+torch.cuda.synchronize()
+print('ok', name)

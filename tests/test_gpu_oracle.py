@@ -207,6 +207,51 @@ def test_segment_reduce_vs_oracle(rua, name, sizes_fn, feat, dtype, fn):
     assert (err <= bound).all(), f'{name}: {fn}: worst excess {float((err - bound).max())}'
 
 
+FLAT_SIZES = {
+    'short': lambda r: r.integers(1, 9, 3000),
+    'empties': lambda r: r.integers(0, 4, 5000),
+    'tile_spanning': lambda r: np.array([5000, 1, 0, 3000, 2, 1025, 1023, 7]),
+    'zipf': lambda r: np.minimum(r.zipf(1.5, 2000), 4096),
+    'one_row': lambda r: np.array([1]),
+    'ragged_tail': lambda r: np.array([3, 1021, 5]),
+}
+
+
+@pytest.mark.parametrize('dtype', [torch.float32, torch.bfloat16, torch.float16, torch.float64])
+@pytest.mark.parametrize('case', sorted(FLAT_SIZES))
+@pytest.mark.parametrize('fn', ['sum', 'mean', 'prod', 'max', 'min', 'logsumexp'])
+def test_flat_segment_reduce_vs_oracle(rua, dtype, case, fn):
+    """featureless data (H == 1): the rows-on-lanes kernel with its block-wide segmented scan; also with a
+    misaligned base pointer (scalar-load path)."""
+    sizes = FLAT_SIZES[case](np.random.default_rng(5)).astype(np.int64)
+    n = int(sizes.sum())
+    g = torch.Generator().manual_seed(9)
+    scale = 0.05 if fn == 'prod' else 1.0
+    base = (torch.randn((n + 1,), generator=g) * scale + (1.0 if fn == 'prod' else 0.0)).to(dtype).cuda()
+    low = dtype in (torch.bfloat16, torch.float16)
+    for shift in (0, 1):
+        data = base[shift:shift + n]
+        got = to_f32(host(getattr(rua, 'segment_' + fn)(data, torch.from_numpy(sizes).cuda())), dtype)
+        x = to_f32(host(data), dtype)
+        exp = ora.REDUCERS[fn](x, sizes)
+        assert got.shape == exp.shape
+        if fn in ('max', 'min'):
+            assert same(got.astype(exp.dtype), exp), f'{case}: {fn} shift {shift}'
+            continue
+        rtol = 1e-2 if low else (1e-12 if dtype == torch.float64 else 1e-5)
+        if fn == 'prod':
+            bound = 20 * rtol * np.abs(exp) + 1e-30
+        else:
+            mag = ora.segment_sum(np.abs(x).astype(np.float64), sizes)
+            if fn == 'mean':
+                mag = mag / np.maximum(sizes, 1)
+            if fn == 'logsumexp':
+                mag = np.ones_like(mag)
+            bound = rtol * np.abs(exp) + rtol * mag
+        err = np.abs(got.astype(np.float64) - exp.astype(np.float64))
+        assert (err <= bound).all(), f'{case}: {fn} shift {shift}: worst excess {float((err - bound).max())}'
+
+
 def test_segment_head_last_vs_oracle(rua):
     rng = np.random.default_rng(3)
     sizes = rng.integers(1, 30, 100).astype(np.int64)

@@ -48,6 +48,25 @@ __device__ __forceinline__ int64_t owner_search(OffFn off, int64_t S, int64_t j)
   return lo;
 }
 
+// The same search done by a whole warp: 32 probes per step instead of 1, so a tile prologue costs
+// ~log32(S) dependent memory round trips instead of log2(S).
+template <typename OffFn>
+__device__ __forceinline__ int64_t warp_owner_search(OffFn off, int64_t S, int64_t j, int lane) {
+  int64_t lo = 0, hi = S;
+  while (hi - lo > 1) {
+    const int64_t n = hi - lo - 1;                 // candidates lo+1 .. hi-1
+    const int64_t step = (n + 31) / 32;
+    const int64_t probe = lo + (int64_t)(lane + 1) * step;
+    const bool ok = probe < hi && off(probe) <= j;
+    const int k = __popc(__ballot_sync(kFullMask, ok));   // probes are monotone: k leading successes
+    const int64_t new_lo = lo + (int64_t)k * step;
+    const int64_t next = new_lo + step;
+    hi = next < hi ? next : hi;
+    lo = new_lo;
+  }
+  return lo;
+}
+
 struct GlobalOff {
   const int64_t* __restrict__ p;
   __device__ __forceinline__ int64_t operator()(int64_t i) const { return __ldg(p + i); }

@@ -20,103 +20,9 @@
 //     extreme is reduced on the fly (one atomic per CTA) and a NaN is detected at emit time; a
 //     third tiny kernel patches empty segments and applies the NaN poisoning.
 #include "reduce_common.cuh"
+#include "reduce_flat.cuh"
 
 namespace rua {
-
-struct RedHeader {            // first 64 bytes of the workspace
-  unsigned long long ext_key; // global min (max / logsumexp) or global max (min), as an order key
-  unsigned int nan_flag;      // a NaN reached an output of max / min / logsumexp
-  unsigned int pad[13];
-};
-
-template <int OP> struct OpInfo {
-  static constexpr bool kIsLse = OP == RUA_LOGSUMEXP;
-  static constexpr bool kNeedsExt = OP == RUA_MAX || OP == RUA_MIN || OP == RUA_LOGSUMEXP;
-  static constexpr int kParts = kIsLse ? 2 : 1;  // accumulator planes (lse keeps max and sum)
-};
-
-// accumulator state for V columns
-template <typename A, int V, int OP>
-struct State {
-  A a[V];   // sum / prod / max / min, or the running max for logsumexp
-  A s[OpInfo<OP>::kIsLse ? V : 1];
-
-  __device__ __forceinline__ void reset() {
-#pragma unroll
-    for (int v = 0; v < V; ++v) {
-      if (OP == RUA_SUM || OP == RUA_MEAN) a[v] = A(0);
-      else if (OP == RUA_PROD) a[v] = A(1);
-      else if (OP == RUA_MIN) a[v] = inf_of<A>();
-      else a[v] = -inf_of<A>();
-      if (OpInfo<OP>::kIsLse) s[v] = A(0);
-    }
-  }
-  template <bool kFast>
-  __device__ __forceinline__ void add(const A* x) {
-#pragma unroll
-    for (int v = 0; v < V; ++v) {
-      if (OP == RUA_SUM || OP == RUA_MEAN) a[v] += x[v];
-      else if (OP == RUA_PROD) a[v] *= x[v];
-      else if (OP == RUA_MAX) a[v] = max_nan(a[v], x[v]);
-      else if (OP == RUA_MIN) a[v] = min_nan(a[v], x[v]);
-      else {  // online logsumexp: one exp per element
-        A d = x[v] - a[v];
-        A e = exp_acc<kFast>(-abs_acc(d));
-        s[v] = d > A(0) ? s[v] * e + A(1) : s[v] + e;
-        a[v] = max_nan(a[v], x[v]);
-      }
-    }
-  }
-  // merge a later piece (b) into this earlier piece, in order
-  template <bool kFast>
-  __device__ __forceinline__ void merge(const State& b) {
-#pragma unroll
-    for (int v = 0; v < V; ++v) {
-      if (OP == RUA_SUM || OP == RUA_MEAN) a[v] += b.a[v];
-      else if (OP == RUA_PROD) a[v] *= b.a[v];
-      else if (OP == RUA_MAX) a[v] = max_nan(a[v], b.a[v]);
-      else if (OP == RUA_MIN) a[v] = min_nan(a[v], b.a[v]);
-      else {
-        A m = max_nan(a[v], b.a[v]);
-        A s1 = s[v] == A(0) ? A(0) : s[v] * exp_acc<kFast>(a[v] - m);
-        A s2 = b.s[v] == A(0) ? A(0) : b.s[v] * exp_acc<kFast>(b.a[v] - m);
-        s[v] = s1 + s2;
-        a[v] = m;
-      }
-    }
-  }
-  __device__ __forceinline__ void finalize(int64_t len, A* out) const {
-#pragma unroll
-    for (int v = 0; v < V; ++v) {
-      if (OP == RUA_MEAN) out[v] = (a[v] != a[v]) ? a[v] : a[v] / (A)len;
-      else if (OP == RUA_LOGSUMEXP) out[v] = log_acc(s[v]) + a[v];
-      else out[v] = a[v];
-    }
-  }
-  __device__ __forceinline__ bool any_nan_out(const A* out) const {
-    bool n = false;
-#pragma unroll
-    for (int v = 0; v < V; ++v) n |= (out[v] != out[v]);
-    return n;
-  }
-};
-
-template <typename A, int V, int OP>
-__device__ __forceinline__ void store_partial(A* base, int64_t H, int64_t col, const State<A, V, OP>& st) {
-#pragma unroll
-  for (int v = 0; v < V; ++v) {
-    base[col + v] = st.a[v];
-    if (OpInfo<OP>::kIsLse) base[H + col + v] = st.s[v];
-  }
-}
-template <typename A, int V, int OP>
-__device__ __forceinline__ void load_partial(const A* base, int64_t H, int64_t col, State<A, V, OP>& st) {
-#pragma unroll
-  for (int v = 0; v < V; ++v) {
-    st.a[v] = base[col + v];
-    if (OpInfo<OP>::kIsLse) st.s[v] = base[H + col + v];
-  }
-}
 
 // ---------------------------------------------------------------------------------------------
 // main kernel
@@ -125,7 +31,7 @@ template <typename T, int V, int OP>
 __global__ void __launch_bounds__(kRedThreads, Store<T>::kMinBlocks)
 segreduce_kernel(const T* __restrict__ data, const int64_t* __restrict__ off, int64_t N, int64_t S, int64_t H,
                  int R, T* __restrict__ out, typename Store<T>::Acc* __restrict__ head,
-                 typename Store<T>::Acc* __restrict__ tail, RedHeader* hdr) {
+                 typename Store<T>::Acc* __restrict__ tail, int64_t* __restrict__ tail_seg, RedHeader* hdr) {
   using A = typename Store<T>::Acc;
   constexpr bool kFast = sizeof(T) == 2;  // 16-bit storage: 1e-2 tolerance, approximate exp is plenty
   constexpr int P = OpInfo<OP>::kParts;
@@ -215,6 +121,8 @@ segreduce_kernel(const T* __restrict__ data, const int64_t* __restrict__ off, in
     }
   }
   if (OpInfo<OP>::kIsLse) ext = min_num(ext, packed_min_to_acc<T, V>(ext2));
+  // tell the span kernel which segment (if any) starts in this chunk and runs past its end
+  if (threadIdx.x == 0 && blockIdx.y == 0) tail_seg[chunk] = (pending && !open) ? s : -1;
   if (pending && active) {
     // the segment continues in the next chunk: whole-chunk pieces go to `head`, suffix pieces to `tail`
     store_partial<A, V, OP>((open ? head : tail) + chunk * P * H, H, col, st);
@@ -254,18 +162,18 @@ template <typename T, int V, int OP>
 __global__ void __launch_bounds__(kRedThreads)
 segreduce_span_kernel(const int64_t* __restrict__ off, int64_t N, int64_t S, int64_t H, int R,
                       T* __restrict__ out, const typename Store<T>::Acc* __restrict__ head,
-                      const typename Store<T>::Acc* __restrict__ tail, RedHeader* hdr) {
+                      const typename Store<T>::Acc* __restrict__ tail, const int64_t* __restrict__ tail_seg,
+                      RedHeader* hdr) {
   using A = typename Store<T>::Acc;
   constexpr bool kFast = sizeof(T) == 2;
   constexpr int P = OpInfo<OP>::kParts;
   const int64_t b = blockIdx.x;            // boundary between chunk b and b+1
-  const int64_t jb = (b + 1) * R;
-  if (jb >= N) return;
-  GlobalOff g{off};
-  const int64_t s = owner_search(g, S, jb);
+  if ((b + 1) * R >= N) return;
+  // the main kernel recorded the segment that starts in chunk b and continues past it (-1: none; a
+  // segment that merely passes THROUGH chunk b is finished by the boundary where it started)
+  const int64_t s = __ldg(tail_seg + b);
+  if (s < 0 || s >= S) return;
   const int64_t beg = __ldg(off + s), end = __ldg(off + s + 1);
-  if (beg >= jb) return;        // a segment starts exactly here: nothing crosses
-  if (beg < b * R) return;      // it began before chunk b: an earlier boundary owns it
   const int64_t col = ((int64_t)blockIdx.y * blockDim.x + threadIdx.x) * V;
   if (col >= H) return;
   State<A, V, OP> acc, piece;
@@ -311,6 +219,8 @@ __global__ void segreduce_init_kernel(RedHeader* hdr, int is_min) {
   hdr->nan_flag = 0u;
 }
 
+static inline size_t tail_seg_bytes(int64_t chunks) { return ((size_t)chunks * sizeof(int64_t) + 15) & ~(size_t)15; }
+
 struct RedPlan {
   int R;
   int64_t chunks;
@@ -318,10 +228,26 @@ struct RedPlan {
   int64_t col_tiles;
   int vec;
   size_t part_elems;  // per partial array
+  bool flat;          // H == 1: rows-on-lanes kernel
+  int vector_loads;
 };
 
 static RedPlan plan_reduce(int64_t N, int64_t H, int32_t dtype, int32_t op, const void* data, const void* out) {
   RedPlan p;
+  p.flat = false;
+  p.vector_loads = 0;
+  if (H == 1) {  // featureless data: rows map to lanes (reduce_flat.cuh); tiles of 256 * (16 / elem) rows
+    int elem = dtype == RUA_F32 ? 4 : (dtype == RUA_F64 ? 8 : 2);
+    p.flat = true;
+    p.vector_loads = (((uintptr_t)data) & 15u) == 0;
+    p.vec = 1;
+    p.threads = 32;
+    p.col_tiles = 1;
+    p.R = kFlatThreads * (16 / elem);
+    p.chunks = N > 0 ? ceil_div(N, p.R) : 0;
+    p.part_elems = (size_t)p.chunks * (op == RUA_LOGSUMEXP ? 2 : 1);
+    return p;
+  }
   int full = dtype == RUA_F32 ? 4 : (dtype == RUA_F64 ? 2 : 8);
   bool aligned = (H % full == 0) && (((uintptr_t)data | (uintptr_t)out) & 15u) == 0;
   p.vec = aligned ? full : 1;
@@ -344,7 +270,8 @@ static int run_reduce(const RedPlan& p, const void* data, const int64_t* off, in
                       void* out, void* ws, cudaStream_t st) {
   using A = typename Store<T>::Acc;
   RedHeader* hdr = (RedHeader*)ws;
-  A* head = (A*)((char*)ws + sizeof(RedHeader));
+  int64_t* tail_seg = (int64_t*)((char*)ws + sizeof(RedHeader));
+  A* head = (A*)((char*)ws + sizeof(RedHeader) + tail_seg_bytes(p.chunks));
   A* tail = head + p.part_elems;
   int rc;
   if (OpInfo<OP>::kNeedsExt) {
@@ -354,11 +281,19 @@ static int run_reduce(const RedPlan& p, const void* data, const int64_t* off, in
   if (N > 0) {
     if (p.col_tiles > 65535) return RUA_ERR_UNSUPPORTED;
     dim3 grid((unsigned)p.chunks, (unsigned)p.col_tiles);
-    segreduce_kernel<T, V, OP><<<grid, p.threads, 0, st>>>((const T*)data, off, N, S, H, p.R, (T*)out, head, tail, hdr);
+    if constexpr (V == 1) {
+      if (p.flat)
+        segreduce_flat_kernel<T, OP><<<(unsigned)p.chunks, kFlatThreads, 0, st>>>((const T*)data, off, N, S, (T*)out,
+                                                                                head, tail, tail_seg, hdr, p.vector_loads);
+      else
+        segreduce_kernel<T, V, OP><<<grid, p.threads, 0, st>>>((const T*)data, off, N, S, H, p.R, (T*)out, head, tail, tail_seg, hdr);
+    } else {
+      segreduce_kernel<T, V, OP><<<grid, p.threads, 0, st>>>((const T*)data, off, N, S, H, p.R, (T*)out, head, tail, tail_seg, hdr);
+    }
     if ((rc = check_launch())) return rc;
     if (p.chunks > 1) {
       dim3 g2((unsigned)(p.chunks - 1), (unsigned)p.col_tiles);
-      segreduce_span_kernel<T, V, OP><<<g2, p.threads, 0, st>>>(off, N, S, H, p.R, (T*)out, head, tail, hdr);
+      segreduce_span_kernel<T, V, OP><<<g2, p.threads, 0, st>>>(off, N, S, H, p.R, (T*)out, head, tail, tail_seg, hdr);
       if ((rc = check_launch())) return rc;
     }
   }
@@ -401,7 +336,8 @@ size_t rua_segment_reduce_workspace_bytes(int64_t N, int64_t S, int64_t H, int32
   RedPlan q = plan_reduce(N, H, dtype, op, (const void*)1, nullptr);
   size_t elems = p.part_elems > q.part_elems ? p.part_elems : q.part_elems;
   size_t acc = dtype == RUA_F64 ? 8 : 4;
-  return sizeof(RedHeader) + 2 * elems * acc + 64;
+  size_t chunks = p.chunks > q.chunks ? p.chunks : q.chunks;
+  return sizeof(RedHeader) + tail_seg_bytes(chunks) + 2 * elems * acc + 64;
 }
 
 int rua_segment_reduce(const void* data, const int64_t* off, int64_t N, int64_t S, int64_t H, int32_t dtype,
@@ -413,7 +349,7 @@ int rua_segment_reduce(const void* data, const int64_t* off, int64_t N, int64_t 
   if (dtype < RUA_F32 || dtype > RUA_BF16) return RUA_ERR_UNSUPPORTED;
   RedPlan p = plan_reduce(N, H, dtype, op, data, out);
   size_t acc = dtype == RUA_F64 ? 8 : 4;
-  if (ws_bytes < sizeof(RedHeader) + 2 * p.part_elems * acc) return RUA_ERR_WORKSPACE;
+  if (ws_bytes < sizeof(RedHeader) + tail_seg_bytes(p.chunks) + 2 * p.part_elems * acc) return RUA_ERR_WORKSPACE;
   if (((uintptr_t)ws & 15u) != 0) return RUA_ERR_INVALID;
   cudaStream_t st = (cudaStream_t)stream;
   switch (dtype) {

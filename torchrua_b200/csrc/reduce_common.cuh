@@ -300,4 +300,103 @@ __device__ __forceinline__ void lse_batch(const Raw<T, V>* raw, typename Store<T
 }
 
 
+// ---------------------------------------------------------------------------------------------
+// per-op accumulator state shared by the wide-row kernel (reduce.cu) and the flat kernel (reduce_flat.cu)
+// ---------------------------------------------------------------------------------------------
+struct RedHeader {            // first 64 bytes of the workspace
+  unsigned long long ext_key; // global min (max / logsumexp) or global max (min), as an order key
+  unsigned int nan_flag;      // a NaN reached an output of max / min / logsumexp
+  unsigned int pad[13];
+};
+
+template <int OP> struct OpInfo {
+  static constexpr bool kIsLse = OP == RUA_LOGSUMEXP;
+  static constexpr bool kNeedsExt = OP == RUA_MAX || OP == RUA_MIN || OP == RUA_LOGSUMEXP;
+  static constexpr int kParts = kIsLse ? 2 : 1;  // accumulator planes (lse keeps max and sum)
+};
+
+// accumulator state for V columns
+template <typename A, int V, int OP>
+struct State {
+  A a[V];   // sum / prod / max / min, or the running max for logsumexp
+  A s[OpInfo<OP>::kIsLse ? V : 1];
+
+  __device__ __forceinline__ void reset() {
+#pragma unroll
+    for (int v = 0; v < V; ++v) {
+      if (OP == RUA_SUM || OP == RUA_MEAN) a[v] = A(0);
+      else if (OP == RUA_PROD) a[v] = A(1);
+      else if (OP == RUA_MIN) a[v] = inf_of<A>();
+      else a[v] = -inf_of<A>();
+      if (OpInfo<OP>::kIsLse) s[v] = A(0);
+    }
+  }
+  template <bool kFast>
+  __device__ __forceinline__ void add(const A* x) {
+#pragma unroll
+    for (int v = 0; v < V; ++v) {
+      if (OP == RUA_SUM || OP == RUA_MEAN) a[v] += x[v];
+      else if (OP == RUA_PROD) a[v] *= x[v];
+      else if (OP == RUA_MAX) a[v] = max_nan(a[v], x[v]);
+      else if (OP == RUA_MIN) a[v] = min_nan(a[v], x[v]);
+      else {  // online logsumexp: one exp per element
+        A d = x[v] - a[v];
+        A e = exp_acc<kFast>(-abs_acc(d));
+        s[v] = d > A(0) ? s[v] * e + A(1) : s[v] + e;
+        a[v] = max_nan(a[v], x[v]);
+      }
+    }
+  }
+  // merge a later piece (b) into this earlier piece, in order
+  template <bool kFast>
+  __device__ __forceinline__ void merge(const State& b) {
+#pragma unroll
+    for (int v = 0; v < V; ++v) {
+      if (OP == RUA_SUM || OP == RUA_MEAN) a[v] += b.a[v];
+      else if (OP == RUA_PROD) a[v] *= b.a[v];
+      else if (OP == RUA_MAX) a[v] = max_nan(a[v], b.a[v]);
+      else if (OP == RUA_MIN) a[v] = min_nan(a[v], b.a[v]);
+      else {
+        A m = max_nan(a[v], b.a[v]);
+        A s1 = s[v] == A(0) ? A(0) : s[v] * exp_acc<kFast>(a[v] - m);
+        A s2 = b.s[v] == A(0) ? A(0) : b.s[v] * exp_acc<kFast>(b.a[v] - m);
+        s[v] = s1 + s2;
+        a[v] = m;
+      }
+    }
+  }
+  __device__ __forceinline__ void finalize(int64_t len, A* out) const {
+#pragma unroll
+    for (int v = 0; v < V; ++v) {
+      if (OP == RUA_MEAN) out[v] = (a[v] != a[v]) ? a[v] : a[v] / (A)len;
+      else if (OP == RUA_LOGSUMEXP) out[v] = log_acc(s[v]) + a[v];
+      else out[v] = a[v];
+    }
+  }
+  __device__ __forceinline__ bool any_nan_out(const A* out) const {
+    bool n = false;
+#pragma unroll
+    for (int v = 0; v < V; ++v) n |= (out[v] != out[v]);
+    return n;
+  }
+};
+
+template <typename A, int V, int OP>
+__device__ __forceinline__ void store_partial(A* base, int64_t H, int64_t col, const State<A, V, OP>& st) {
+#pragma unroll
+  for (int v = 0; v < V; ++v) {
+    base[col + v] = st.a[v];
+    if (OpInfo<OP>::kIsLse) base[H + col + v] = st.s[v];
+  }
+}
+template <typename A, int V, int OP>
+__device__ __forceinline__ void load_partial(const A* base, int64_t H, int64_t col, State<A, V, OP>& st) {
+#pragma unroll
+  for (int v = 0; v < V; ++v) {
+    st.a[v] = base[col + v];
+    if (OpInfo<OP>::kIsLse) st.s[v] = base[H + col + v];
+  }
+}
+
+
 }  // namespace rua

@@ -68,6 +68,8 @@ __device__ __forceinline__ int64_t pack_shift(const rua_side_t& sd) {
   return sd.len_xform == RUA_LEN_MINUS ? sd.len_arg : 0;
 }
 
+__device__ __forceinline__ int64_t source_row(const RowMapParams& p, int64_t i, int64_t td, int64_t base_len);
+
 // destination row j -> source row (or kPadRow)
 __device__ __forceinline__ int64_t map_row(const RowMapParams& p, int64_t j) {
   const rua_ragged_t& rg = p.rg;
@@ -101,7 +103,12 @@ __device__ __forceinline__ int64_t map_row(const RowMapParams& p, int64_t j) {
     if (td < 0 || td >= ld) return kPadRow;
   }
   if (!have_len) base_len = __ldg(rg.off + i + 1) - __ldg(rg.off + i);
+  return source_row(p, i, td, base_len);
+}
 
+// token (i, t_d) of the destination -> source row (or kPadRow): token map, validity, source layout
+__device__ __forceinline__ int64_t source_row(const RowMapParams& p, int64_t i, int64_t td, int64_t base_len) {
+  const rua_ragged_t& rg = p.rg;
   int64_t ts;
   if (p.tmap == RUA_MAP_SHIFT) {
     ts = td + p.tmap_arg;
@@ -227,10 +234,148 @@ row_map_kernel(const RowMapParams p) {
   }
 }
 
-inline int pow2_floor(int64_t x) {
-  int p = 1;
-  while ((int64_t)p * 2 <= x) p *= 2;
-  return p;
+// ------------------------------------------------------------------------------------------------
+// narrow rows (< 128 bytes: token ids, indices, scalars -- BASELINE config 5).  A 20-step binary
+// search per 8-byte row would dominate, so here a CTA owns a TILE of consecutive destination
+// vectors: one warp-cooperative 32-ary search per tile end finds the segments (sequences or time
+// steps) that intersect the tile, their offsets are staged in shared memory, and every thread
+// resolves its row with a short shared-memory search.  One thread moves one vector; consecutive
+// lanes touch consecutive addresses on the destination side.
+// ------------------------------------------------------------------------------------------------
+constexpr int kTileThreads = 256;
+constexpr int kTileItems = 8;
+constexpr int kTileVecs = kTileThreads * kTileItems;  // 2048 destination vectors per CTA
+constexpr int kTileCap = kTileVecs + 2;               // staged segment starts
+
+template <typename V, typename OffFn>
+__device__ __forceinline__ void tile_body(const RowMapParams& p, OffFn f, int64_t S, int64_t* s_off,
+                                          int64_t* s_bounds) {
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int64_t total = p.d.rows * p.row_vecs;
+  const int64_t e0 = (int64_t)blockIdx.x * kTileVecs;
+  const int64_t e1 = e0 + kTileVecs < total ? e0 + kTileVecs : total;
+  const int64_t r0 = e0 / p.row_vecs, r1 = (e1 - 1) / p.row_vecs;  // first / last destination row of the tile
+  if (warp == 0) {
+    int64_t a = warp_owner_search(f, S, r0, lane);
+    if (lane == 0) s_bounds[0] = a;
+  } else if (warp == 1) {
+    int64_t b = warp_owner_search(f, S, r1, lane);
+    if (lane == 0) s_bounds[1] = b;
+  }
+  __syncthreads();
+  const int64_t first = s_bounds[0], last = s_bounds[1];
+  const int64_t cnt = last - first + 2;          // f(first) .. f(last + 1)
+  const bool staged = cnt <= kTileCap;           // runs of empty segments can overflow the stage
+  if (staged)
+    for (int64_t k = tid; k < cnt; k += kTileThreads) s_off[k] = f(first + k);
+  __syncthreads();
+
+  const V* __restrict__ src = reinterpret_cast<const V*>(p.src);
+  V* __restrict__ dst = reinterpret_cast<V*>(p.dst);
+  const bool is_pack = p.d.layout == RUA_PACK;
+  int64_t srow[kTileItems];
+  int64_t col[kTileItems];
+#pragma unroll
+  for (int r = 0; r < kTileItems; ++r) {
+    const int64_t e = e0 + (int64_t)r * kTileThreads + tid;
+    srow[r] = kNoRow;
+    if (e < e1) {
+      const int64_t j = e / p.row_vecs;
+      col[r] = e - j * p.row_vecs;
+      int64_t s, base;
+      if (staged) {
+        int lo = 0, hi = (int)(cnt - 1);
+        while (hi - lo > 1) {
+          const int mid = (lo + hi) >> 1;
+          if (s_off[mid] <= j) lo = mid; else hi = mid;
+        }
+        s = first + lo;
+        base = s_off[lo];
+      } else {
+        s = owner_search(f, S, j);
+        base = f(s);
+      }
+      int64_t i, td;
+      if (is_pack) { td = s; i = __ldg(p.rg.sorted + (j - base)); }
+      else { i = s; td = j - base; }
+      const int64_t base_len = __ldg(p.rg.off + i + 1) - __ldg(p.rg.off + i);
+      int64_t sr = source_row(p, i, td, base_len);
+      if (sr == kPadRow && p.pad_mode == RUA_PAD_ROW0) sr = 0;
+      srow[r] = sr;
+    }
+  }
+  V val[kTileItems];
+#pragma unroll
+  for (int r = 0; r < kTileItems; ++r)
+    if (srow[r] >= 0) val[r] = ld_stream(src + srow[r] * p.row_vecs + col[r]);
+#pragma unroll
+  for (int r = 0; r < kTileItems; ++r) {
+    const int64_t e = e0 + (int64_t)r * kTileThreads + tid;
+    if (srow[r] >= 0) st_stream(dst + e, val[r]);
+    else if (srow[r] == kPadRow) st_stream(dst + e, make_fill<V>(p.fill, col[r] * (int64_t)sizeof(V)));
+  }
+}
+
+// destination C or P: segment search through shared memory
+template <typename V>
+__global__ void __launch_bounds__(kTileThreads)
+row_map_tile_kernel(const RowMapParams p) {
+  __shared__ int64_t s_off[kTileCap];
+  __shared__ int64_t s_bounds[2];
+  if (p.d.layout == RUA_CAT) {
+    CatOff f{p.rg.off, p.d.len_xform, p.d.len_arg};
+    tile_body<V>(p, f, p.rg.B, s_off, s_bounds);
+  } else {
+    const int64_t sh = pack_shift(p.d);
+    PackOff f{p.rg.poff, sh};
+    const int64_t steps = p.d.len_xform == RUA_LEN_CONST ? p.d.len_arg : p.rg.Tp - sh;
+    tile_body<V>(p, f, steps, s_off, s_bounds);
+  }
+}
+
+// destination L or R (and the explicit-index gather/scatter): the decode is arithmetic, no staging
+template <typename V>
+__global__ void __launch_bounds__(kTileThreads)
+row_map_flat_kernel(const RowMapParams p) {
+  const int64_t total = p.d.rows * p.row_vecs;
+  const int64_t e0 = (int64_t)blockIdx.x * kTileVecs;
+  const V* __restrict__ src = reinterpret_cast<const V*>(p.src);
+  V* __restrict__ dst = reinterpret_cast<V*>(p.dst);
+  int64_t srow[kTileItems], drow[kTileItems], col[kTileItems];
+#pragma unroll
+  for (int r = 0; r < kTileItems; ++r) {
+    const int64_t e = e0 + (int64_t)r * kTileThreads + threadIdx.x;
+    srow[r] = kNoRow;
+    if (e < total) {
+      int64_t j;
+      if (total < (1ll << 31)) { j = (uint32_t)e / (uint32_t)p.row_vecs; } else { j = e / p.row_vecs; }
+      col[r] = e - j * p.row_vecs;
+      drow[r] = j;
+      int64_t sr;
+      if (p.gather_index) { sr = __ldg(p.gather_index + j); if (sr < 0) sr += p.s.rows; }
+      else if (p.scatter_index) { sr = j; int64_t d = __ldg(p.scatter_index + j); drow[r] = d < 0 ? d + p.s.rows : d; }
+      else sr = map_row(p, j);
+      if (sr == kPadRow && p.pad_mode == RUA_PAD_ROW0) sr = 0;
+      srow[r] = sr;
+    }
+  }
+  V val[kTileItems];
+#pragma unroll
+  for (int r = 0; r < kTileItems; ++r)
+    if (srow[r] >= 0) val[r] = ld_stream(src + srow[r] * p.row_vecs + col[r]);
+#pragma unroll
+  for (int r = 0; r < kTileItems; ++r) {
+    if (srow[r] >= 0) st_stream(dst + drow[r] * p.row_vecs + col[r], val[r]);
+    else if (srow[r] == kPadRow) st_stream(dst + drow[r] * p.row_vecs + col[r], make_fill<V>(p.fill, col[r] * (int64_t)sizeof(V)));
+  }
+}
+
+template <typename V>
+static void launch_narrow(const RowMapParams& p, int64_t rows, cudaStream_t st) {
+  const int64_t blocks = ceil_div(rows * p.row_vecs, kTileVecs);
+  const bool searched = !p.gather_index && !p.scatter_index && (p.d.layout == RUA_CAT || p.d.layout == RUA_PACK);
+  if (searched) row_map_tile_kernel<V><<<(unsigned)blocks, kTileThreads, 0, st>>>(p);
+  else row_map_flat_kernel<V><<<(unsigned)blocks, kTileThreads, 0, st>>>(p);
 }
 
 static int launch_row_map(RowMapParams& p, int64_t row_bytes, int64_t rows, cudaStream_t st) {
@@ -240,6 +385,18 @@ static int launch_row_map(RowMapParams& p, int64_t row_bytes, int64_t rows, cuda
   int vec = 16;
   while (vec > 1 && (a & (uintptr_t)(vec - 1))) vec >>= 1;
   p.row_vecs = row_bytes / vec;
+
+  if (row_bytes < 128) {  // narrow rows: tile kernels (segment offsets staged in shared memory)
+    if (ceil_div(rows * p.row_vecs, kTileVecs) >= (1ll << 31)) return RUA_ERR_UNSUPPORTED;
+    switch (vec) {
+      case 16: launch_narrow<uint4>(p, rows, st); break;
+      case 8: launch_narrow<uint2>(p, rows, st); break;
+      case 4: launch_narrow<unsigned int>(p, rows, st); break;
+      case 2: launch_narrow<unsigned short>(p, rows, st); break;
+      default: launch_narrow<unsigned char>(p, rows, st); break;
+    }
+    return check_launch();
+  }
 
   // lanes per row: short rows share a warp (32/lpr rows move concurrently)
   int lpr = 1;

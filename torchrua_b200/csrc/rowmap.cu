@@ -248,13 +248,19 @@ constexpr int kTileVecs = kTileThreads * kTileItems;  // 2048 destination vector
 constexpr int kTileCap = kTileVecs + 2;               // staged segment starts
 
 template <typename V, typename OffFn>
-__device__ __forceinline__ void tile_body(const RowMapParams& p, OffFn f, int64_t S, int64_t* s_off,
+__device__ __forceinline__ void tile_body(const RowMapParams& p, OffFn f, int64_t S, int* s_rel,
                                           int64_t* s_bounds) {
+  // Everything inside a tile is 32-bit and tile-relative (a tile spans 2048 vectors): these kernels are
+  // ISSUE-bound (ncu: 65 % issue-active at 19 % DRAM), so 64-bit divisions and 64-bit shared-memory
+  // searches are what they cannot afford.
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int64_t total = p.d.rows * p.row_vecs;
   const int64_t e0 = (int64_t)blockIdx.x * kTileVecs;
-  const int64_t e1 = e0 + kTileVecs < total ? e0 + kTileVecs : total;
-  const int64_t r0 = e0 / p.row_vecs, r1 = (e1 - 1) / p.row_vecs;  // first / last destination row of the tile
+  const int n_e = (int)(e0 + kTileVecs < total ? kTileVecs : total - e0);  // vectors in this tile
+  const uint32_t rv = (uint32_t)p.row_vecs;                                 // < 8 (rows are < 128 bytes)
+  const int64_t r0 = rv == 1 ? e0 : e0 / rv;                                // first destination row
+  const uint32_t c0 = rv == 1 ? 0u : (uint32_t)(e0 - r0 * rv);              // column of the first vector
+  const int64_t r1 = rv == 1 ? e0 + n_e - 1 : (e0 + n_e - 1) / rv;          // last destination row
   if (warp == 0) {
     int64_t a = warp_owner_search(f, S, r0, lane);
     if (lane == 0) s_bounds[0] = a;
@@ -264,41 +270,54 @@ __device__ __forceinline__ void tile_body(const RowMapParams& p, OffFn f, int64_
   }
   __syncthreads();
   const int64_t first = s_bounds[0], last = s_bounds[1];
-  const int64_t cnt = last - first + 2;          // f(first) .. f(last + 1)
-  const bool staged = cnt <= kTileCap;           // runs of empty segments can overflow the stage
-  if (staged)
-    for (int64_t k = tid; k < cnt; k += kTileThreads) s_off[k] = f(first + k);
+  const int64_t cnt64 = last - first + 2;        // f(first) .. f(last + 1)
+  const bool staged = cnt64 <= kTileCap;         // runs of empty segments can overflow the stage
+  const int cnt = staged ? (int)cnt64 : 0;
+  if (staged) {
+    for (int k = tid; k < cnt; k += kTileThreads) {
+      int64_t d = f(first + k) - r0;             // tile-relative start of segment first+k
+      s_rel[k] = d < -1 ? -1 : (d > kTileVecs + 1 ? kTileVecs + 1 : (int)d);
+    }
+  }
   __syncthreads();
 
   const V* __restrict__ src = reinterpret_cast<const V*>(p.src);
-  V* __restrict__ dst = reinterpret_cast<V*>(p.dst);
+  V* __restrict__ dst = reinterpret_cast<V*>(p.dst) + e0;
   const bool is_pack = p.d.layout == RUA_PACK;
+  const bool len_from_stage = staged && !is_pack && p.d.len_xform == RUA_LEN_SAME;
   int64_t srow[kTileItems];
-  int64_t col[kTileItems];
+  uint32_t col[kTileItems];
 #pragma unroll
   for (int r = 0; r < kTileItems; ++r) {
-    const int64_t e = e0 + (int64_t)r * kTileThreads + tid;
+    const int e = r * kTileThreads + tid;        // vector index inside the tile
     srow[r] = kNoRow;
-    if (e < e1) {
-      const int64_t j = e / p.row_vecs;
-      col[r] = e - j * p.row_vecs;
+    col[r] = 0;
+    if (e < n_e) {
+      uint32_t jr;                               // tile-relative destination row
+      if (rv == 1) { jr = (uint32_t)e; }
+      else { const uint32_t q = (uint32_t)e + c0; jr = q / rv; col[r] = q - jr * rv; }
       int64_t s, base;
+      int64_t base_len = -1;
       if (staged) {
-        int lo = 0, hi = (int)(cnt - 1);
+        int lo = 0, hi = cnt - 1;
         while (hi - lo > 1) {
           const int mid = (lo + hi) >> 1;
-          if (s_off[mid] <= j) lo = mid; else hi = mid;
+          if (s_rel[mid] <= (int)jr) lo = mid; else hi = mid;
         }
         s = first + lo;
-        base = s_off[lo];
+        base = r0 + s_rel[lo];                   // exact: s_rel[lo] <= jr means it was not clamped high,
+                                                 // and only segment `first` can start before the tile
+        if (lo == 0) base = f(first);
+        if (len_from_stage && lo > 0 && s_rel[lo + 1] <= kTileVecs) base_len = s_rel[lo + 1] - s_rel[lo];
       } else {
-        s = owner_search(f, S, j);
+        s = owner_search(f, S, r0 + jr);
         base = f(s);
       }
+      const int64_t j = r0 + jr;
       int64_t i, td;
       if (is_pack) { td = s; i = __ldg(p.rg.sorted + (j - base)); }
       else { i = s; td = j - base; }
-      const int64_t base_len = __ldg(p.rg.off + i + 1) - __ldg(p.rg.off + i);
+      if (base_len < 0) base_len = __ldg(p.rg.off + i + 1) - __ldg(p.rg.off + i);
       int64_t sr = source_row(p, i, td, base_len);
       if (sr == kPadRow && p.pad_mode == RUA_PAD_ROW0) sr = 0;
       srow[r] = sr;
@@ -307,12 +326,12 @@ __device__ __forceinline__ void tile_body(const RowMapParams& p, OffFn f, int64_
   V val[kTileItems];
 #pragma unroll
   for (int r = 0; r < kTileItems; ++r)
-    if (srow[r] >= 0) val[r] = ld_stream(src + srow[r] * p.row_vecs + col[r]);
+    if (srow[r] >= 0) val[r] = ld_stream(src + (rv == 1 ? srow[r] : srow[r] * rv + col[r]));
 #pragma unroll
   for (int r = 0; r < kTileItems; ++r) {
-    const int64_t e = e0 + (int64_t)r * kTileThreads + tid;
+    const int e = r * kTileThreads + tid;
     if (srow[r] >= 0) st_stream(dst + e, val[r]);
-    else if (srow[r] == kPadRow) st_stream(dst + e, make_fill<V>(p.fill, col[r] * (int64_t)sizeof(V)));
+    else if (srow[r] == kPadRow) st_stream(dst + e, make_fill<V>(p.fill, (int64_t)col[r] * (int64_t)sizeof(V)));
   }
 }
 
@@ -320,16 +339,16 @@ __device__ __forceinline__ void tile_body(const RowMapParams& p, OffFn f, int64_
 template <typename V>
 __global__ void __launch_bounds__(kTileThreads)
 row_map_tile_kernel(const RowMapParams p) {
-  __shared__ int64_t s_off[kTileCap];
+  __shared__ int s_rel[kTileCap];
   __shared__ int64_t s_bounds[2];
   if (p.d.layout == RUA_CAT) {
     CatOff f{p.rg.off, p.d.len_xform, p.d.len_arg};
-    tile_body<V>(p, f, p.rg.B, s_off, s_bounds);
+    tile_body<V>(p, f, p.rg.B, s_rel, s_bounds);
   } else {
     const int64_t sh = pack_shift(p.d);
     PackOff f{p.rg.poff, sh};
     const int64_t steps = p.d.len_xform == RUA_LEN_CONST ? p.d.len_arg : p.rg.Tp - sh;
-    tile_body<V>(p, f, steps, s_off, s_bounds);
+    tile_body<V>(p, f, steps, s_rel, s_bounds);
   }
 }
 

@@ -252,6 +252,32 @@ def test_flat_segment_reduce_vs_oracle(rua, dtype, case, fn):
         assert (err <= bound).all(), f'{case}: {fn} shift {shift}: worst excess {float((err - bound).max())}'
 
 
+@pytest.mark.parametrize('dtype', [torch.float32, torch.bfloat16, torch.float16, torch.float64])
+@pytest.mark.parametrize('width', [2, 4, 8, 3])
+@pytest.mark.parametrize('fn', ['sum', 'mean', 'max', 'min', 'logsumexp'])
+def test_narrow_segment_reduce_vs_oracle(rua, dtype, width, fn):
+    """rows of 2/4/8 elements (<= 16 bytes: rows-on-lanes kernels) and 3 (generic path) against the oracle."""
+    rng = np.random.default_rng(21)
+    sizes = np.concatenate([rng.integers(0, 6, 700), [3000, 1, 0, 1500], rng.integers(1, 40, 100)]).astype(np.int64)
+    n = int(sizes.sum())
+    data = torch.randn((n, width), generator=torch.Generator().manual_seed(13)).to(dtype).cuda()
+    got = to_f32(host(getattr(rua, 'segment_' + fn)(data, torch.from_numpy(sizes).cuda())), dtype)
+    x = to_f32(host(data), dtype)
+    exp = ora.REDUCERS[fn](x, sizes)
+    if fn in ('max', 'min'):
+        assert same(got.astype(exp.dtype), exp)
+        return
+    low = dtype in (torch.bfloat16, torch.float16)
+    rtol = 1e-2 if low else (1e-12 if dtype == torch.float64 else 1e-5)
+    mag = ora.segment_sum(np.abs(x).astype(np.float64), sizes)
+    if fn == 'mean':
+        mag = mag / np.maximum(sizes, 1)[:, None]
+    if fn == 'logsumexp':
+        mag = np.ones_like(mag)
+    err = np.abs(got.astype(np.float64) - exp.astype(np.float64))
+    assert (err <= rtol * np.abs(exp) + rtol * mag).all()
+
+
 def test_segment_head_last_vs_oracle(rua):
     rng = np.random.default_rng(3)
     sizes = rng.integers(1, 30, 100).astype(np.int64)

@@ -20,9 +20,15 @@
 //     extreme is reduced on the fly (one atomic per CTA) and a NaN is detected at emit time; a
 //     third tiny kernel patches empty segments and applies the NaN poisoning.
 #include "reduce_common.cuh"
-#include "reduce_flat.cuh"
 
 namespace rua {
+
+// narrow rows (H * elem <= 16 bytes) run on the rows-on-lanes kernels of reduce_flat.cu
+bool flat_supported(int32_t dtype, int64_t H);
+int flat_rows_per_tile(int32_t dtype, int64_t H);
+int flat_launch(int32_t dtype, int64_t H, int32_t op, const void* data, const int64_t* off, int64_t N, int64_t S,
+                void* out, void* head, void* tail, int64_t* tail_seg, void* hdr, int vector_loads, int64_t tiles,
+                cudaStream_t st);
 
 // ---------------------------------------------------------------------------------------------
 // main kernel
@@ -228,24 +234,25 @@ struct RedPlan {
   int64_t col_tiles;
   int vec;
   size_t part_elems;  // per partial array
-  bool flat;          // H == 1: rows-on-lanes kernel
+  bool flat;          // narrow rows: rows-on-lanes kernel
   int vector_loads;
+  int32_t dtype;
 };
 
 static RedPlan plan_reduce(int64_t N, int64_t H, int32_t dtype, int32_t op, const void* data, const void* out) {
   RedPlan p;
   p.flat = false;
   p.vector_loads = 0;
-  if (H == 1) {  // featureless data: rows map to lanes (reduce_flat.cuh); tiles of 256 * (16 / elem) rows
-    int elem = dtype == RUA_F32 ? 4 : (dtype == RUA_F64 ? 8 : 2);
+  p.dtype = dtype;
+  if (flat_supported(dtype, H)) {  // narrow rows: rows map to lanes (reduce_flat.cu)
     p.flat = true;
     p.vector_loads = (((uintptr_t)data) & 15u) == 0;
     p.vec = 1;
     p.threads = 32;
     p.col_tiles = 1;
-    p.R = kFlatThreads * (16 / elem);
+    p.R = flat_rows_per_tile(dtype, H);
     p.chunks = N > 0 ? ceil_div(N, p.R) : 0;
-    p.part_elems = (size_t)p.chunks * (op == RUA_LOGSUMEXP ? 2 : 1);
+    p.part_elems = (size_t)p.chunks * (size_t)H * (op == RUA_LOGSUMEXP ? 2 : 1);
     return p;
   }
   int full = dtype == RUA_F32 ? 4 : (dtype == RUA_F64 ? 2 : 8);
@@ -281,16 +288,13 @@ static int run_reduce(const RedPlan& p, const void* data, const int64_t* off, in
   if (N > 0) {
     if (p.col_tiles > 65535) return RUA_ERR_UNSUPPORTED;
     dim3 grid((unsigned)p.chunks, (unsigned)p.col_tiles);
-    if constexpr (V == 1) {
-      if (p.flat)
-        segreduce_flat_kernel<T, OP><<<(unsigned)p.chunks, kFlatThreads, 0, st>>>((const T*)data, off, N, S, (T*)out,
-                                                                                head, tail, tail_seg, hdr, p.vector_loads);
-      else
-        segreduce_kernel<T, V, OP><<<grid, p.threads, 0, st>>>((const T*)data, off, N, S, H, p.R, (T*)out, head, tail, tail_seg, hdr);
+    if (p.flat) {
+      rc = flat_launch(p.dtype, H, OP, data, off, N, S, out, head, tail, tail_seg, hdr, p.vector_loads, p.chunks, st);
+      if (rc) return rc;
     } else {
       segreduce_kernel<T, V, OP><<<grid, p.threads, 0, st>>>((const T*)data, off, N, S, H, p.R, (T*)out, head, tail, tail_seg, hdr);
+      if ((rc = check_launch())) return rc;
     }
-    if ((rc = check_launch())) return rc;
     if (p.chunks > 1) {
       dim3 g2((unsigned)(p.chunks - 1), (unsigned)p.col_tiles);
       segreduce_span_kernel<T, V, OP><<<g2, p.threads, 0, st>>>(off, N, S, H, p.R, (T*)out, head, tail, tail_seg, hdr);

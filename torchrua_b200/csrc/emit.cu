@@ -56,54 +56,102 @@ mask_kernel(const int64_t* __restrict__ len, int64_t B, int64_t W, E zero, E one
 // shared-memory binary search instead of a log2(S)-deep walk over global memory.
 // ------------------------------------------------------------------------------------------------
 constexpr int kEmitThreads = 256;
-constexpr int kEmitItems = 8;
-constexpr int kEmitTile = kEmitThreads * kEmitItems;  // 2048 positions per CTA
-constexpr int kEmitCap = kEmitTile + 2;               // segment starts staged per tile
+constexpr int kEmitGroup = 4;                                   // consecutive positions per thread = one 256-bit store
+constexpr int kEmitRounds = 2;
+constexpr int kEmitTile = kEmitThreads * kEmitGroup * kEmitRounds;  // 2048 positions per CTA
+constexpr int kEmitCap = kEmitTile + 2;                            // segment starts staged per tile
+
+// sm_100a has 256-bit global stores (SASS STG.E.ENL2.256): one full 32-byte sector per lane
+__device__ __forceinline__ void st_v4_i64(int64_t* p, const int64_t* v) {
+  asm volatile("st.global.v4.b64 [%0], {%1, %2, %3, %4};" ::"l"(p), "l"(v[0]), "l"(v[1]), "l"(v[2]), "l"(v[3]) : "memory");
+}
 
 __global__ void __launch_bounds__(kEmitThreads)
 emit_ptr_kernel(const int64_t* __restrict__ off, int64_t S, int64_t n, const int64_t* __restrict__ relabel,
                 int64_t* __restrict__ which, int64_t* __restrict__ within, int64_t* __restrict__ flat,
-                int64_t stride, int right_align) {
-  __shared__ int64_t s_off[kEmitCap];
+                int64_t stride, int right_align, int wide_stores) {
+  __shared__ int s_rel[kEmitCap];          // tile-relative segment starts, clamped to [-1, tile + 1]
   __shared__ int64_t s_first, s_last;
   const int tid = threadIdx.x;
   const int64_t j0 = (int64_t)blockIdx.x * kEmitTile;
-  const int64_t j1 = j0 + kEmitTile < n ? j0 + kEmitTile : n;
+  const int nj = (int)(j0 + kEmitTile < n ? kEmitTile : n - j0);
   GlobalOff g{off};
-  if (tid == 0) s_first = owner_search(g, S, j0);
-  if (tid == 32) s_last = owner_search(g, S, j1 - 1);
-  __syncthreads();
-  const int64_t first = s_first, last = s_last;
-  const int64_t cnt = last - first + 2;  // off[first .. last+1]
-  const bool staged = cnt <= kEmitCap;   // many empty segments inside the tile can overflow the stage
-  if (staged) {
-    for (int64_t k = tid; k < cnt; k += kEmitThreads) s_off[k] = __ldg(off + first + k);
+  // two warp-cooperative 32-ary searches (log32 S dependent round trips instead of log2 S)
+  if (tid < 32) {
+    const int64_t a = warp_owner_search(g, S, j0, tid);
+    if (tid == 0) s_first = a;
+  } else if (tid < 64) {
+    const int64_t b = warp_owner_search(g, S, j0 + nj - 1, tid - 32);
+    if (tid == 32) s_last = b;
   }
   __syncthreads();
+  const int64_t first = s_first, last = s_last;
+  const int64_t cnt64 = last - first + 2;  // off[first .. last+1]
+  const bool staged = cnt64 <= kEmitCap;   // many empty segments inside the tile can overflow the stage
+  const int cnt = staged ? (int)cnt64 : 0;
+  if (staged) {
+    for (int k = tid; k < cnt; k += kEmitThreads) {
+      const int64_t d = __ldg(off + first + k) - j0;
+      s_rel[k] = d < -1 ? -1 : (d > kEmitTile + 1 ? kEmitTile + 1 : (int)d);
+    }
+  }
+  __syncthreads();
+  const int64_t off_first = __ldg(off + first);  // the only staged start that can lie before the tile
 
 #pragma unroll
-  for (int r = 0; r < kEmitItems; ++r) {
-    const int64_t j = j0 + (int64_t)r * kEmitThreads + tid;
-    if (j >= j1) break;
-    int64_t s, base, next;
+  for (int r = 0; r < kEmitRounds; ++r) {
+    const int jb = (r * kEmitThreads + tid) * kEmitGroup;  // tile-relative, 4 consecutive positions
+    if (jb >= nj) break;
+    int64_t sv[kEmitGroup], wv[kEmitGroup], fv[kEmitGroup];
     if (staged) {
-      int lo = 0, hi = (int)(cnt - 1);
+      int lo = 0, hi = cnt - 1;              // one search for the group's first position ...
       while (hi - lo > 1) {
-        int mid = (lo + hi) >> 1;
-        if (s_off[mid] <= j) lo = mid; else hi = mid;
+        const int mid = (lo + hi) >> 1;
+        if (s_rel[mid] <= jb) lo = mid; else hi = mid;
       }
-      s = first + lo;
-      base = s_off[lo];
-      next = s_off[lo + 1];
+#pragma unroll
+      for (int k = 0; k < kEmitGroup; ++k) {  // ... then walk: a group rarely crosses more than one boundary
+        const int jr = jb + k;
+        while (lo + 2 < cnt && s_rel[lo + 1] <= jr) ++lo;
+        const int64_t base = lo == 0 ? off_first : j0 + s_rel[lo];
+        const int64_t j = j0 + jr;
+        sv[k] = first + lo;
+        wv[k] = j - base;
+        if (flat) {
+          const int64_t len = (s_rel[lo + 1] <= kEmitTile && lo > 0) ? (int64_t)(s_rel[lo + 1] - s_rel[lo])
+                                                                      : __ldg(off + first + lo + 1) - base;
+          fv[k] = sv[k] * stride + wv[k] + (right_align ? stride - len : 0);
+        }
+      }
     } else {
-      s = owner_search(g, S, j);
-      base = __ldg(off + s);
-      next = __ldg(off + s + 1);
+#pragma unroll
+      for (int k = 0; k < kEmitGroup; ++k) {
+        const int64_t j = j0 + jb + k;
+        const int64_t jj = j < n ? j : n - 1;
+        const int64_t s = owner_search(g, S, jj);
+        const int64_t base = __ldg(off + s);
+        sv[k] = s;
+        wv[k] = jj - base;
+        fv[k] = s * stride + wv[k] + (right_align ? stride - (__ldg(off + s + 1) - base) : 0);
+      }
     }
-    const int64_t w = j - base;
-    if (which) __stcs(which + j, s);
-    if (within) __stcs(within + j, relabel ? __ldg(relabel + w) : w);
-    if (flat) __stcs(flat + j, s * stride + w + (right_align ? stride - (next - base) : 0));
+    if (relabel) {
+#pragma unroll
+      for (int k = 0; k < kEmitGroup; ++k)
+        if (jb + k < nj) wv[k] = __ldg(relabel + wv[k]);
+    }
+    const int64_t j = j0 + jb;
+    if (wide_stores && jb + kEmitGroup <= nj) {
+      if (which) st_v4_i64(which + j, sv);
+      if (within) st_v4_i64(within + j, wv);
+      if (flat) st_v4_i64(flat + j, fv);
+    } else {
+      for (int k = 0; k < kEmitGroup && jb + k < nj; ++k) {
+        if (which) which[j + k] = sv[k];
+        if (within) within[j + k] = wv[k];
+        if (flat) flat[j + k] = fv[k];
+      }
+    }
   }
 }
 
@@ -142,8 +190,10 @@ int rua_emit_ptr(const int64_t* off, int64_t S, int64_t n, const int64_t* relabe
   if (!which && !within && !flat) return RUA_OK;
   const int64_t blocks = ceil_div(n, kEmitTile);
   if (blocks >= (1ll << 31)) return RUA_ERR_UNSUPPORTED;
+  const uintptr_t align = (uintptr_t)which | (uintptr_t)within | (uintptr_t)flat;
   emit_ptr_kernel<<<(unsigned)blocks, kEmitThreads, 0, (cudaStream_t)stream>>>(off, S, n, relabel, which, within,
-                                                                            flat, stride, right_align);
+                                                                            flat, stride, right_align,
+                                                                            (align & 31u) == 0);
   return check_launch();
 }
 

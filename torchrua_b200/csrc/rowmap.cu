@@ -14,6 +14,8 @@
 // lane.  Padding is written by the same pass, so every output byte is stored exactly once and no
 // payload byte is read twice: traffic = N*D read + rows_dst*D written (+ metadata).
 // HBM-bound; no shared memory (no reuse) and no tensor cores (nothing to contract).
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace rua {
@@ -152,6 +154,20 @@ __device__ __forceinline__ int64_t source_row(const RowMapParams& p, int64_t i, 
 template <typename V> __device__ __forceinline__ V ld_stream(const V* p) { return __ldcs(p); }
 template <typename V> __device__ __forceinline__ void st_stream(V* p, V v) { __stcs(p, v); }
 
+// 256-bit global accesses are new with sm_100 (SASS LDG.E.ENL2.256 / STG.E.ENL2.256): one full 32-byte
+// sector per lane and half the LSU instructions of the 128-bit form.  Used when rows are 32-byte multiples.
+struct alignas(32) V256 {
+  unsigned long long x, y, z, w;
+};
+template <> __device__ __forceinline__ V256 ld_stream<V256>(const V256* p) {
+  V256 v;
+  asm volatile("ld.global.cs.v4.b64 {%0, %1, %2, %3}, [%4];" : "=l"(v.x), "=l"(v.y), "=l"(v.z), "=l"(v.w) : "l"(p));
+  return v;
+}
+template <> __device__ __forceinline__ void st_stream<V256>(V256* p, V256 v) {
+  asm volatile("st.global.cs.v4.b64 [%0], {%1, %2, %3, %4};" ::"l"(p), "l"(v.x), "l"(v.y), "l"(v.z), "l"(v.w) : "memory");
+}
+
 // the fill pattern is replicated over 16 bytes; a vector narrower than the element (possible only
 // for oddly aligned views) picks the slice that matches its byte offset within the row
 __device__ __forceinline__ uint32_t fill_word(const uint4& f, int w) {
@@ -159,6 +175,10 @@ __device__ __forceinline__ uint32_t fill_word(const uint4& f, int w) {
 }
 template <typename V> __device__ __forceinline__ V make_fill(const uint4& f, int64_t byte_off);
 template <> __device__ __forceinline__ uint4 make_fill<uint4>(const uint4& f, int64_t) { return f; }
+template <> __device__ __forceinline__ V256 make_fill<V256>(const uint4& f, int64_t) {
+  const unsigned long long lo = ((unsigned long long)f.y << 32) | f.x, hi = ((unsigned long long)f.w << 32) | f.z;
+  return V256{lo, hi, lo, hi};
+}
 template <> __device__ __forceinline__ uint2 make_fill<uint2>(const uint4& f, int64_t o) {
   int w = (int)((o >> 2) & 2);
   return make_uint2(fill_word(f, w), fill_word(f, w + 1));
@@ -218,13 +238,14 @@ row_map_kernel(const RowMapParams p) {
     V* drow_p = dst + dj * p.row_vecs;
     if (s >= 0) {
       const V* srow_p = src + s * p.row_vecs;
+      constexpr int U = sizeof(V) >= 32 ? kUnroll / 2 : kUnroll;   // 64 bytes in flight per lane either way
       int64_t c = c0 + l;
-      for (; c + (int64_t)(kUnroll - 1) * lpr < c1; c += (int64_t)kUnroll * lpr) {
-        V v[kUnroll];
+      for (; c + (int64_t)(U - 1) * lpr < c1; c += (int64_t)U * lpr) {
+        V v[U];
 #pragma unroll
-        for (int u = 0; u < kUnroll; ++u) v[u] = ld_stream(srow_p + c + (int64_t)u * lpr);
+        for (int u = 0; u < U; ++u) v[u] = ld_stream(srow_p + c + (int64_t)u * lpr);
 #pragma unroll
-        for (int u = 0; u < kUnroll; ++u) st_stream(drow_p + c + (int64_t)u * lpr, v[u]);
+        for (int u = 0; u < U; ++u) st_stream(drow_p + c + (int64_t)u * lpr, v[u]);
       }
       for (; c < c1; c += lpr) st_stream(drow_p + c, ld_stream(srow_p + c));
     } else {
@@ -401,7 +422,8 @@ static int launch_row_map(RowMapParams& p, int64_t row_bytes, int64_t rows, cuda
   if (rows <= 0 || row_bytes <= 0) return RUA_OK;
   // widest vector that divides the row size and both base addresses
   uintptr_t a = (uintptr_t)p.src | (uintptr_t)p.dst | (uintptr_t)row_bytes;
-  int vec = 16;
+  static const bool use256 = [] { const char* e = getenv("RUA_VEC256"); return !(e && e[0] == '0'); }();
+  int vec = (use256 && row_bytes >= 128) ? 32 : 16;   // 256-bit accesses only in the wide-row kernel
   while (vec > 1 && (a & (uintptr_t)(vec - 1))) vec >>= 1;
   p.row_vecs = row_bytes / vec;
 
@@ -436,6 +458,7 @@ static int launch_row_map(RowMapParams& p, int64_t row_bytes, int64_t rows, cuda
   if (blocks >= (1ll << 31)) return RUA_ERR_UNSUPPORTED;
   dim3 grid((unsigned)blocks, (unsigned)splits);
   switch (vec) {
+    case 32: row_map_kernel<V256><<<grid, kRowMapThreads, 0, st>>>(p); break;
     case 16: row_map_kernel<uint4><<<grid, kRowMapThreads, 0, st>>>(p); break;
     case 8: row_map_kernel<uint2><<<grid, kRowMapThreads, 0, st>>>(p); break;
     case 4: row_map_kernel<unsigned int><<<grid, kRowMapThreads, 0, st>>>(p); break;

@@ -96,7 +96,9 @@ def time_cpu(steps: int, warmup: int, budget_s: float):
 # clocks sampler (nvidia-smi during the timed region)
 # --------------------------------------------------------------------------------------------------
 class Clocks:
-    QUERY = ('index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,'
+    """nvidia-smi sampler.  Started before the warm-up (its start-up latency is longer than a short timed
+    region); only samples whose timestamps fall inside the marked timed region are reported."""
+    QUERY = ('timestamp,index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,'
              'clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,'
              'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
 
@@ -104,6 +106,7 @@ class Clocks:
         self.index = index
         self.path = tempfile.mktemp(prefix='rua_clocks_', suffix='.csv')
         self.proc = None
+        self.t_begin = self.t_end = None
 
     def start(self):
         try:
@@ -114,38 +117,51 @@ class Clocks:
         except Exception:
             self.proc = None
 
+    def begin(self):
+        self.t_begin = time.time()
+
+    def end(self):
+        self.t_end = time.time()
+
     def stop(self):
+        import datetime
         out = {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': [], 'samples': 0}
         if self.proc is None:
             return out
-        time.sleep(0.15)
+        time.sleep(0.05)
         self.proc.terminate()
         try:
             self.proc.wait(timeout=5)
         except Exception:
             self.proc.kill()
         self.fp.close()
-        sm, mx, reasons = [], [], set()
         names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        rows = []
         for line in open(self.path):
             f = [x.strip() for x in line.split(',')]
-            if len(f) < 9:
+            if len(f) < 10:
                 continue
             try:
-                sm.append(float(f[1]))
-                mx.append(float(f[2]))
+                ts = datetime.datetime.strptime(f[0], '%Y/%m/%d %H:%M:%S.%f').timestamp()
+                rows.append((ts, float(f[2]), float(f[3]), [n for n, v in zip(names, f[6:10]) if v.lower().startswith('active')]))
             except ValueError:
                 continue
-            for name, val in zip(names, f[5:9]):
-                if val.lower().startswith('active'):
-                    reasons.add(name)
         try:
             os.unlink(self.path)
         except OSError:
             pass
-        if sm:
-            busy = sorted(sm)[len(sm) // 2:]      # upper half = samples taken under load
-            out.update(sm_mhz=statistics.median(busy), sm_max_mhz=max(mx), reasons=sorted(reasons), samples=len(sm))
+        if not rows:
+            return out
+        lo, hi = (self.t_begin or 0) - 0.005, (self.t_end or 1e18) + 0.005
+        inside = [r for r in rows if lo <= r[0] <= hi]
+        where = 'inside the timed region'
+        if not inside:   # region shorter than the sampling period: take the sample closest to it
+            mid = 0.5 * (lo + hi)
+            inside = [min(rows, key=lambda r: abs(r[0] - mid))]
+            where = 'nearest to the timed region (region shorter than the 20 ms sampling period)'
+        reasons = sorted({n for r in inside for n in r[3]})
+        out.update(sm_mhz=statistics.median(r[1] for r in inside), sm_max_mhz=max(r[2] for r in inside),
+                   reasons=reasons, samples=len(inside), where=where)
         return out
 
 
@@ -207,15 +223,19 @@ def run_ours(args):
 
     def step(d, ln):
         _native._CACHE.clear()                      # no metadata survives from one step to the next
-        if world > 1:                               # the only collective: 8 bytes per sequence of metadata
-            shard.all_gather_lengths_fixed(ln, cap, gathered)
+        work = None
         c = rua.C(data=d, token_sizes=ln)
         p = c.pack()
+        if world > 1:                               # the only collective: 8 bytes per sequence of metadata; issued
+            # while the first row-map kernel runs, so neither its host-side enqueue nor NCCL is on the critical path
+            work = shard.all_gather_lengths_fixed(ln, cap, gathered, async_op=True)
         left = p.left(0)
         right = left.right(0)
         back = right.cat()
         s = rua.segment_sum(back.data, back.token_sizes)
         m = rua.segment_max(back.data, back.token_sizes)
+        if work is not None:
+            work.wait()                             # stream-ordered: the step is not done before the exchange is
         return back, s, m
 
     def barrier():
@@ -224,13 +244,14 @@ def run_ours(args):
         torch.cuda.synchronize()
 
     # ---- warm-up, then the device-timed region -----------------------------------------------------
+    clocks = Clocks(local)
+    clocks.start()
     for _ in range(max(args.warmup, 3)):
         out = step(data, lens)
     assert torch.equal(out[0].data, data), 'round trip C->P->L->R->C is not the identity'
     del out
-    clocks = Clocks(local)
     barrier()
-    clocks.start()
+    clocks.begin()
     _native.PROFILE = []
     launches0 = lib.rua_launch_count()
     t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -239,6 +260,7 @@ def run_ours(args):
         step(data, lens)
     t1.record()
     barrier()
+    clocks.end()
     launches = lib.rua_launch_count() - launches0
     prof, _native.PROFILE = _native.PROFILE, None
     clk = clocks.stop()

@@ -66,14 +66,15 @@ def all_gather_lengths(local_lengths: Tensor, group: Optional[dist.ProcessGroup]
 
 
 def all_gather_lengths_fixed(local_lengths: Tensor, cap: int, out: Tensor,
-                             group: Optional[dist.ProcessGroup] = None) -> Tensor:
+                             group: Optional[dist.ProcessGroup] = None, async_op: bool = False):
     """single-collective variant for steady-state loops: ``out`` is (world, cap+1); row r = [count_r,
-    lengths_r..., 0 padding]."""
+    lengths_r..., 0 padding].  With ``async_op`` the collective is returned as a work handle so that it
+    overlaps the local kernels (nothing on a rank's own data path waits for the other ranks' lengths)."""
     buf = torch.zeros(cap + 1, dtype=torch.long, device=local_lengths.device)
     buf[0] = local_lengths.numel()
     buf[1:1 + local_lengths.numel()] = local_lengths
-    dist.all_gather_into_tensor(out.view(-1), buf, group=group)
-    return out
+    work = dist.all_gather_into_tensor(out.view(-1), buf, group=group, async_op=async_op)
+    return work if async_op else out
 
 
 def gather_rows_by_sequence(local_rows: Tensor, parts: List[Tensor], group: Optional[dist.ProcessGroup] = None

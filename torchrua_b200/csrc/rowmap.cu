@@ -410,11 +410,176 @@ row_map_flat_kernel(const RowMapParams p) {
   }
 }
 
+// destination L or R with narrow rows: the decode is arithmetic, but a 64-bit division and two global
+// length loads per 8-byte element are still too many instructions.  A CTA owns 2048 consecutive
+// destination vectors = a run of consecutive sequences; their offsets are staged once in shared memory
+// (tile-relative, 32-bit), and every thread needs one 32-bit division by a CTA-uniform constant.
+template <typename V>
+__global__ void __launch_bounds__(kTileThreads)
+row_map_padded_kernel(const RowMapParams p) {
+  __shared__ int s_rel[kTileCap];            // off[i0 + k] - off[i0]; clamped only beyond the tile's reach
+  const int tid = threadIdx.x;
+  const int64_t total = p.d.rows * p.row_vecs;
+  const int64_t e0 = (int64_t)blockIdx.x * kTileVecs;
+  const int n_e = (int)(e0 + kTileVecs < total ? kTileVecs : total - e0);
+  const uint32_t rv = (uint32_t)p.row_vecs;
+  const int64_t wrv64 = p.d.width * p.row_vecs;   // vectors per padded sequence
+  const int64_t i0 = e0 / wrv64;                  // first sequence of the tile (one 64-bit division per CTA)
+  const int64_t i1 = (e0 + n_e - 1) / wrv64;
+  const int64_t head64 = e0 - i0 * wrv64;         // offset of the tile's first vector inside sequence i0
+  const int cnt = (int)(i1 - i0 + 2);             // <= 2050 because every sequence holds >= 1 vector
+  const int64_t base0 = __ldg(p.rg.off + i0);
+  for (int k = tid; k < cnt; k += kTileThreads) {
+    const int64_t d = __ldg(p.rg.off + i0 + k) - base0;
+    s_rel[k] = d > (1 << 30) ? (1 << 30) : (int)d;   // lengths >= 2^30 only matter as "longer than the width"
+  }
+  __syncthreads();
+  // when a padded row is longer than the tile, (head + e) can exceed 32 bits only if wrv64 does: then the
+  // tile lies inside ONE sequence and the quotient is 0
+  const bool one_seq = wrv64 > (int64_t)(1u << 30);
+  const uint32_t wrv = one_seq ? 1u : (uint32_t)wrv64;
+  const uint32_t head = one_seq ? 0u : (uint32_t)head64;
+  const uint32_t width = (uint32_t)(p.d.width < (1ll << 31) ? p.d.width : (1ll << 31) - 1);
+
+  const V* __restrict__ src = reinterpret_cast<const V*>(p.src);
+  V* __restrict__ dst = reinterpret_cast<V*>(p.dst) + e0;
+  int64_t srow[kTileItems];
+  uint32_t col[kTileItems];
+#pragma unroll
+  for (int r = 0; r < kTileItems; ++r) {
+    const int e = r * kTileThreads + tid;
+    srow[r] = kNoRow;
+    col[r] = 0;
+    if (e < n_e) {
+      uint32_t q, t, c;
+      if (one_seq) {
+        const int64_t rem = head64 + e;
+        q = 0;
+        t = (uint32_t)(rem / rv);
+        c = (uint32_t)(rem - (int64_t)t * rv);
+      } else {
+        const uint32_t x = head + (uint32_t)e;
+        q = x / wrv;
+        const uint32_t rem = x - q * wrv;
+        if (rv == 1) { t = rem; c = 0; } else { t = rem / rv; c = rem - t * rv; }
+      }
+      col[r] = c;
+      const int64_t base_len = (int64_t)s_rel[q + 1] - (int64_t)s_rel[q];   // exact unless >= 2^30 (then > width anyway)
+      const int64_t ld = side_len(p.d, base_len);
+      int64_t td = t;
+      if (p.d.layout == RUA_RIGHT) td -= ((int64_t)width - ld);
+      int64_t sr = kPadRow;
+      if (td >= 0 && td < ld) sr = source_row(p, i0 + q, td, base_len);
+      if (sr == kPadRow && p.pad_mode == RUA_PAD_ROW0) sr = 0;
+      srow[r] = sr;
+    }
+  }
+  V val[kTileItems];
+#pragma unroll
+  for (int r = 0; r < kTileItems; ++r)
+    if (srow[r] >= 0) val[r] = ld_stream(src + (rv == 1 ? srow[r] : srow[r] * rv + col[r]));
+#pragma unroll
+  for (int r = 0; r < kTileItems; ++r) {
+    const int e = r * kTileThreads + tid;
+    if (srow[r] >= 0) st_stream(dst + e, val[r]);
+    else if (srow[r] == kPadRow) st_stream(dst + e, make_fill<V>(p.fill, (int64_t)col[r] * (int64_t)sizeof(V)));
+  }
+}
+
+// P <-> {C, L, R} with one-vector rows (<= 16 bytes: token ids, scalars).  P is time-major, the other
+// layouts are sequence-major: moving 8-byte rows one by one leaves one side with 8 useful bytes per
+// 32-byte sector.  This is a ragged TRANSPOSE instead: a CTA owns a 32 (ranks) x 32 (time steps) tile,
+// touches P along ranks (contiguous for a fixed t) and the other layout along time (contiguous for a
+// fixed sequence), and swaps the roles through a padded shared-memory tile.  Tiles that lie entirely
+// beyond the ragged frontier (batch_sizes[t0] <= r0) exit at once.
+template <typename V, bool kFromPack>
+__global__ void __launch_bounds__(256)
+row_map_transpose_kernel(const RowMapParams p) {
+  __shared__ V tile[32][33];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int64_t r0 = (int64_t)blockIdx.x * 32, t0 = (int64_t)blockIdx.y * 32;
+  const rua_side_t& sq = kFromPack ? p.d : p.s;     // the sequence-major side
+  const int64_t B = p.rg.B, Tp = p.rg.Tp, W = sq.width;
+  const int64_t* __restrict__ poff = p.rg.poff;
+  const int64_t* __restrict__ off = p.rg.off;
+  const bool padded_dst = kFromPack && sq.layout != RUA_CAT;
+  const int64_t bs0 = t0 < Tp ? __ldg(poff + t0 + 1) - __ldg(poff + t0) : 0;
+  if (!padded_dst && bs0 <= r0) return;             // CTA-uniform: no token of this tile exists
+  const V* __restrict__ src = reinterpret_cast<const V*>(p.src);
+  V* __restrict__ dst = reinterpret_cast<V*>(p.dst);
+
+  auto pack_phase = [&](const bool load) {           // lanes run over ranks: contiguous rows of P
+    for (int tt = warp; tt < 32; tt += 8) {
+      const int64_t t = t0 + tt;
+      if (t >= Tp) break;
+      const int64_t pt = __ldg(poff + t), bst = __ldg(poff + t + 1) - pt;
+      const int64_t r = r0 + lane;
+      if (r < bst) {
+        if (load) tile[tt][lane] = ld_stream(src + pt + r);
+        else st_stream(dst + pt + r, tile[tt][lane]);
+      }
+    }
+  };
+  auto seq_phase = [&](const bool load) {            // lanes run over time: contiguous rows of one sequence
+    for (int rr = warp; rr < 32; rr += 8) {
+      const int64_t r = r0 + rr;
+      if (r >= B) break;
+      const int64_t i = __ldg(p.rg.sorted + r);
+      const int64_t o = __ldg(off + i), len = __ldg(off + i + 1) - o;
+      const int64_t t = t0 + lane;
+      int64_t row;
+      if (sq.layout == RUA_CAT) row = o + t;
+      else if (sq.layout == RUA_LEFT) row = i * W + t;
+      else row = i * W + (W - len) + t;
+      if (load) {
+        if (t < len) tile[lane][rr] = ld_stream(src + row);
+      } else if (t < len) {
+        st_stream(dst + row, tile[lane][rr]);
+      } else if (padded_dst && t < W) {              // left-aligned padding (R destinations do not come here)
+        st_stream(dst + i * W + t, make_fill<V>(p.fill, 0));
+      }
+    }
+  };
+  if (kFromPack) {
+    pack_phase(true);
+    __syncthreads();
+    seq_phase(false);
+  } else {
+    seq_phase(true);
+    __syncthreads();
+    pack_phase(false);
+  }
+}
+
+// can the ragged transpose serve this call?  (identity token map, untransformed lengths, one vector per row)
+static bool transpose_applies(const RowMapParams& p, int64_t* grid_y) {
+  if (p.gather_index || p.scatter_index || p.row_vecs != 1) return false;
+  if (p.tmap != RUA_MAP_SHIFT || p.tmap_arg != 0 || p.pad_mode != RUA_PAD_FILL) return false;
+  if (p.s.len_xform != RUA_LEN_SAME || p.d.len_xform != RUA_LEN_SAME) return false;
+  const bool from_pack = p.s.layout == RUA_PACK && p.d.layout != RUA_PACK;
+  const bool to_pack = p.d.layout == RUA_PACK && p.s.layout != RUA_PACK;
+  if (!from_pack && !to_pack) return false;
+  if (from_pack && p.d.layout == RUA_RIGHT) return false;   // right-aligned padding is not tile-aligned
+  int64_t t_extent = p.rg.Tp;
+  if (from_pack && p.d.layout == RUA_LEFT && p.d.width > t_extent) t_extent = p.d.width;
+  *grid_y = ceil_div(t_extent, 32);
+  return *grid_y >= 1 && *grid_y <= 65535 && ceil_div(p.rg.B, 32) < (1ll << 31);
+}
+
 template <typename V>
 static void launch_narrow(const RowMapParams& p, int64_t rows, cudaStream_t st) {
+  int64_t gy = 0;
+  if (transpose_applies(p, &gy)) {
+    dim3 grid((unsigned)ceil_div(p.rg.B, 32), (unsigned)gy);
+    if (p.s.layout == RUA_PACK) row_map_transpose_kernel<V, true><<<grid, 256, 0, st>>>(p);
+    else row_map_transpose_kernel<V, false><<<grid, 256, 0, st>>>(p);
+    return;
+  }
   const int64_t blocks = ceil_div(rows * p.row_vecs, kTileVecs);
-  const bool searched = !p.gather_index && !p.scatter_index && (p.d.layout == RUA_CAT || p.d.layout == RUA_PACK);
+  const bool indexed = p.gather_index || p.scatter_index;
+  const bool searched = !indexed && (p.d.layout == RUA_CAT || p.d.layout == RUA_PACK);
   if (searched) row_map_tile_kernel<V><<<(unsigned)blocks, kTileThreads, 0, st>>>(p);
+  else if (!indexed) row_map_padded_kernel<V><<<(unsigned)blocks, kTileThreads, 0, st>>>(p);
   else row_map_flat_kernel<V><<<(unsigned)blocks, kTileThreads, 0, st>>>(p);
 }
 

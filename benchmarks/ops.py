@@ -106,6 +106,35 @@ def cfg2(results, reps):
             lc = lens.cuda()
             aten = lambda fn=fn, lc=lc: torch.segment_reduce(data, fn, lengths=lc, unsafe=True)
         row(results, 2, f'segment_{fn}', nd + b * d + 8 * b, n, lambda f=f: f(data, c.token_sizes), reps, aten)
+    # scatter_* ("next" row 8f-1): the same rows in a random order, reduced by an unsorted index
+    perm = torch.randperm(n, device='cuda')
+    idx = torch.repeat_interleave(torch.arange(b, device='cuda'), lens.cuda())[perm]
+    src = data[perm]
+    base = torch.zeros((b, 1024), device='cuda', dtype=torch.bfloat16)
+    row(results, 2, 'scatter_sum (unsorted)', nd + b * d + 16 * n, n, lambda: rua.scatter_sum(base, idx, src), reps,
+        lambda: torch.index_add(base, 0, idx, src))
+    row(results, 2, 'scatter_max (unsorted)', nd + b * d + 16 * n, n, lambda: rua.scatter_max(base, idx, src), reps,
+        lambda: torch.index_reduce(base, 0, idx, src, 'amax', include_self=False))
+    del perm, idx, src, base
+    # backward passes (api time of .backward() alone; the forward graph is rebuilt outside the timed region)
+    leaf = data.clone().requires_grad_(True)
+    lc = lens.cuda()
+
+    def bwd(build, nbytes, name, aten_build=None):
+        def make(bf):
+            out = bf()
+            gout = torch.ones_like(out)
+            return lambda: torch.autograd.grad(out, leaf, gout, retain_graph=True)
+        row(results, 2, name, nbytes, n, make(build), reps, make(aten_build) if aten_build else None)
+
+    cl = rua.C(data=leaf, token_sizes=lc)
+    bwd(lambda: cl.pack().data, 2 * nd, 'bwd C->P')
+    bwd(lambda: cl.left(0).data, nd + btd, 'bwd C->L')
+    bwd(lambda: rua.segment_sum(leaf, lc), nd + b * d, 'bwd segment_sum',
+        lambda: torch.segment_reduce(leaf, 'sum', lengths=lc, unsafe=True))
+    bwd(lambda: rua.segment_max(leaf, lc), 3 * nd + 2 * b * d, 'bwd segment_max',
+        lambda: torch.segment_reduce(leaf, 'max', lengths=lc, unsafe=True))
+    bwd(lambda: rua.segment_logsumexp(leaf, lc), 2 * nd + 2 * b * d, 'bwd segment_logsumexp')
 
 
 def cfg3(results, reps):

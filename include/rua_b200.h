@@ -119,6 +119,14 @@ size_t rua_sort_workspace_bytes(int64_t B);
 int rua_sort_lengths(const int64_t* len, int64_t B, int64_t T, int64_t* sorted, int64_t* unsorted,
                      void* ws, size_t ws_bytes, rua_stream_t stream);
 
+/* stable ASCENDING argsort of int64 keys in [0, max_key] and its inverse (scatter_* sort their index
+ * with this; same workspace as rua_sort_lengths), and the bucket boundaries of the sorted order:
+ * off[m] = #{k : keys[k] < m} for m in [0, M]. */
+int rua_sort_keys(const int64_t* keys, int64_t n, int64_t max_key, int64_t* sorted, int64_t* unsorted,
+                  void* ws, size_t ws_bytes, rua_stream_t stream);
+int rua_bucket_offsets(const int64_t* keys, const int64_t* sorted, int64_t n, int64_t M, int64_t* off,
+                       rua_stream_t stream);
+
 /* out[perm[j]] = j */
 int rua_invert_permutation(const int64_t* perm, int64_t B, int64_t* out, rua_stream_t stream);
 
@@ -196,6 +204,13 @@ size_t rua_segment_reduce_workspace_bytes(int64_t N, int64_t S, int64_t H, int32
 int rua_segment_reduce(const void* data, const int64_t* off, int64_t N, int64_t S, int64_t H,
                        int32_t dtype, int32_t op, void* out, void* ws, size_t ws_bytes,
                        rua_stream_t stream);
+
+/* the same reduction over GATHERED rows: segment s reduces data[row_index[r]] for r in [off[s], off[s+1]);
+ * N = off[S] = number of entries of row_index.  scatter_* (torchrua/reduce.py:6-31) = stable sort of the
+ * index + rua_bucket_offsets + this. */
+int rua_segment_reduce_gather(const void* data, const int64_t* row_index, const int64_t* off, int64_t N,
+                              int64_t S, int64_t H, int32_t dtype, int32_t op, void* out, void* ws,
+                              size_t ws_bytes, rua_stream_t stream);
 
 /* backward twin (ATen SegmentReduceBackward0 semantics): sum -> broadcast, mean ->
  * broadcast / len, max/min -> split evenly among ties, prod -> grad*out/x (exact when x != 0, else

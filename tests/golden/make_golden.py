@@ -246,6 +246,57 @@ def main():
     save('ties_2000', rec)
 
 
+def compose_case():
+    """compose(list of ragged batches in mixed layouts) -> P; stored in canonical (cat) form, plus split()"""
+    rec = Rec()
+    g = torch.Generator().manual_seed(6)
+    batches = []
+    for b, kind in enumerate('CLPR'):
+        lens = torch.randint(1, 7, (3 + b,), generator=g)
+        data = torch.randn((int(lens.sum()), 3), generator=g)
+        rec.put(f'in{b}.data', data, True)
+        rec.put(f'in{b}.token_sizes', lens, True)
+        batches.append(build(kind, C(data=data, token_sizes=lens)))
+    out = rua.compose(batches)
+    rec.put_seq('out', out, True)
+    cat = out.cat()
+    rec.put_seq('out.cat', cat, True)
+    for k, piece in enumerate(batches[2].split()):
+        rec.put(f'split2.{k}', piece, True)
+    for k, piece in enumerate(batches[1].split()):
+        rec.put(f'split1.{k}', piece, True)
+    rec.put('tolist3', np.asarray([len(x) for x in batches[3].tolist()], dtype=np.int64), True)
+    save('compose_f32', rec)
+
+
+def scatter_case():
+    """scatter_{sum,mean,prod,max,min,logsumexp}: forward and gradients, include_self on/off, with rows of
+    `tensor` that no index points at."""
+    rec = Rec()
+    g = torch.Generator().manual_seed(8)
+    m, k, h = 9, 40, 3
+    index = torch.randint(0, m - 2, (k,), generator=g)      # rows m-2, m-1 stay untouched
+    index[index == 3] = 4                                   # and so does row 3
+    tensor = torch.randn((m, h), generator=g)
+    source = torch.randn((k, h), generator=g)
+    weight = torch.randn((m, h), generator=g)
+    rec.put('index', index, True)
+    rec.put('tensor', tensor, True)
+    rec.put('source', source, True)
+    rec.put('weight', weight, True)
+    for op in ('sum', 'mean', 'prod', 'max', 'min', 'logsumexp'):
+        for inc in (False, True):
+            t = tensor.clone().requires_grad_(True)
+            s = (source * 0.3 + 1.0 if op == 'prod' else source).clone().requires_grad_(True)
+            out = getattr(rua, 'scatter_' + op)(t, index, s, include_self=inc)
+            gt, gs = torch.autograd.grad((out * weight)[torch.isfinite(out)].sum(), [t, s], allow_unused=True)
+            tag = f'{op}.{int(inc)}'
+            rec.put(tag + '.out', out, True)
+            rec.put(tag + '.grad_tensor', gt if gt is not None else torch.zeros_like(t), True)
+            rec.put(tag + '.grad_source', gs if gs is not None else torch.zeros_like(s), True)
+    save('scatter_f32', rec)
+
+
 def api_surface():
     """public names of the reference package and the methods bound on the four layouts"""
     skip = {'Any', 'List', 'Tuple', 'Union', 'Number', 'NamedTuple', 'Tensor', 'PackedSequence', 'torch', 'Key',
@@ -269,4 +320,6 @@ def api_surface():
 
 if __name__ == '__main__':
     main()
+    compose_case()
+    scatter_case()
     api_surface()

@@ -224,6 +224,57 @@ def test_seg(rua):
         assert (host(out.cat().data) == ref).all()
 
 
+def test_compose_split_tolist(rua):
+    """compose() of four ragged batches in C/L/P/R layouts (-> one PackedSequence), split() and tolist():
+    the rows just outside the hot path, compared in canonical (cat) form with the reference's outputs."""
+    g = Golden('compose_f32')
+    build = {'C': lambda z: z, 'L': lambda z: z.left(0), 'R': lambda z: z.right(0), 'P': lambda z: z.pack()}
+    batches = []
+    for b, kind in enumerate('CLPR'):
+        c = rua.C(data=dev(g[f'in{b}.data']), token_sizes=dev(g[f'in{b}.token_sizes']))
+        batches.append(build[kind](c))
+    out = rua.compose(batches)
+    g.check('out.batch_sizes', host(out.batch_sizes))
+    cat = out.cat()
+    g.check('out.cat.token_sizes', host(cat.token_sizes))
+    g.check('out.cat.data', host(cat.data))
+    assert (host(out.unsorted_indices)[host(out.sorted_indices)] == np.arange(out.sorted_indices.numel())).all()
+    for k, piece in enumerate(batches[2].split()):
+        g.check(f'split2.{k}', host(piece))
+    for k, piece in enumerate(batches[1].split()):
+        g.check(f'split1.{k}', host(piece))
+    g.check('tolist3', np.asarray([len(x) for x in batches[3].tolist()], dtype=np.int64))
+
+
+@pytest.mark.parametrize('op', ['sum', 'mean', 'prod', 'max', 'min', 'logsumexp'])
+@pytest.mark.parametrize('include_self', [False, True])
+def test_scatter_reductions(rua, op, include_self):
+    """scatter_* (unsorted-index reductions, 'next' row 8f-1): forward and both gradients against the
+    reference.  max/min are bit-exact; the sums follow the fp32 tolerance (rtol 1e-5, atol 1e-5)."""
+    g = Golden('scatter_f32')
+    index = dev(g['index'])
+    weight = dev(g['weight'])
+    t = dev(g['tensor']).requires_grad_(True)
+    src = g['source'] * np.float32(0.3) + np.float32(1.0) if op == 'prod' else g['source']
+    s = dev(src).requires_grad_(True)
+    out = getattr(rua, 'scatter_' + op)(t, index, s, include_self=include_self)
+    tag = f'{op}.{int(include_self)}'
+    exact = op in ('max', 'min')
+    g.check(tag + '.out', host(out), exact=exact, rtol=1e-5, atol=1e-5)
+    gt, gs = torch.autograd.grad((out * weight)[torch.isfinite(out)].sum(), [t, s], allow_unused=True)
+    gt = torch.zeros_like(t) if gt is None else gt
+    gs = torch.zeros_like(s) if gs is None else gs
+    g.check(tag + '.grad_tensor', host(gt), exact=False, rtol=1e-5, atol=1e-5)
+    g.check(tag + '.grad_source', host(gs), exact=False, rtol=1e-4, atol=1e-5)
+    # other dims and an integer payload (ATen composition, like the reference)
+    if op == 'sum':
+        out_t = rua.scatter_sum(t.detach().t().contiguous(), index, s.detach().t().contiguous(), include_self, dim=1)
+        np.testing.assert_allclose(host(out_t.t()), g[tag + '.out'], rtol=1e-5, atol=1e-5)
+        ints = rua.scatter_sum(torch.zeros(9, dtype=torch.long, device='cuda'), index,
+                               torch.ones(40, dtype=torch.long, device='cuda'))
+        assert int(ints.sum()) == 40
+
+
 def test_tie_order_contract(rua):
     """SURVEY.md 8c hazard 1 on the CUDA path: (i) batch_sizes bit-equal, (ii) sorted lengths equal and
     the permutation consistent, (iii) canonical equality, (iv) bit-identical data with the reference's

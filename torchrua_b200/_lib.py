@@ -39,6 +39,10 @@ SIGNATURES = {
     'rua_scan_lengths': (c_int32, [c_void_p, c_int64, c_int64, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
     'rua_sort_workspace_bytes': (c_size_t, [c_int64]),
     'rua_sort_lengths': (c_int32, [c_void_p, c_int64, c_int64, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
+    'rua_sort_keys': (c_int32, [c_void_p, c_int64, c_int64, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
+    'rua_bucket_offsets': (c_int32, [c_void_p, c_void_p, c_int64, c_int64, c_void_p, c_void_p]),
+    'rua_segment_reduce_gather': (c_int32, [c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int64, c_int32, c_int32,
+                                            c_void_p, c_void_p, c_size_t, c_void_p]),
     'rua_invert_permutation': (c_int32, [c_void_p, c_int64, c_void_p, c_void_p]),
     'rua_batch_sizes': (c_int32, [c_void_p, c_void_p, c_int64, c_int64, c_void_p, c_void_p]),
     'rua_lengths_from_pack': (c_int32, [c_void_p, c_void_p, c_int64, c_int64, c_void_p, c_void_p]),

@@ -612,3 +612,106 @@ def segment_reduce(data: Tensor, segment_sizes: Tensor, op: str) -> Tensor:
     if not (data.requires_grad and torch.is_grad_enabled()):
         return _reduce_raw(data if data.is_contiguous() else data.contiguous(), rg.off, rg.B, _OPS[op])
     return _SegmentReduce.apply(data, rg.off, rg.B, _OPS[op])
+
+
+# ------------------------------------------------------------------------------------------------
+# scatter_*: stable sort of the index + bucket boundaries + segment reduce over GATHERED rows
+# ------------------------------------------------------------------------------------------------
+def sort_keys(keys: Tensor, max_key: int) -> Tuple[Tensor, Tensor]:
+    """stable ascending argsort of int64 keys in [0, max_key] (device radix sort) and its inverse."""
+    lib = _lib.load()
+    keys = _i64(keys)
+    require_cuda(keys)
+    n = keys.numel()
+    srt = torch.empty(n, dtype=torch.long, device=keys.device)
+    uns = torch.empty(n, dtype=torch.long, device=keys.device)
+    if n > 0:
+        with _on(keys.device):
+            nbytes = lib.rua_sort_workspace_bytes(n)
+            ws = torch.empty(nbytes, dtype=torch.uint8, device=keys.device)
+            _lib.check(lib.rua_sort_keys(keys.data_ptr(), n, max(max_key, 0), srt.data_ptr(), uns.data_ptr(),
+                                         ws.data_ptr(), nbytes, _stream()), 'rua_sort_keys')
+    return srt, uns
+
+
+def bucket_offsets(keys: Tensor, srt: Tensor, buckets: int) -> Tensor:
+    """off[m] = #{k : keys[k] < m} for m in [0, buckets], given the ascending permutation of the keys."""
+    lib = _lib.load()
+    keys = _i64(keys)
+    off = torch.empty(buckets + 1, dtype=torch.long, device=keys.device)
+    with _on(keys.device):
+        _lib.check(lib.rua_bucket_offsets(_ptr(keys), _ptr(srt), keys.numel(), buckets, off.data_ptr(), _stream()),
+                   'rua_bucket_offsets')
+    return off
+
+
+def _reduce_gather_raw(data: Tensor, row_index: Tensor, off: Tensor, S: int, op: int) -> Tensor:
+    lib = _lib.load()
+    if data.dtype not in _DTYPES:
+        raise RuntimeError(f'torchrua_b200: scatter reductions support float16/bfloat16/float32/float64, got {data.dtype}')
+    N = row_index.numel()
+    feat = tuple(data.shape[1:])
+    H = 1
+    for f in feat:
+        H *= f
+    out = torch.empty((S,) + feat, dtype=data.dtype, device=data.device)
+    if out.numel() == 0:
+        return out
+    dt = _DTYPES[data.dtype]
+    with _on(data.device):
+        nbytes = lib.rua_segment_reduce_workspace_bytes(N, S, H, dt, op)
+        ws = torch.empty(nbytes, dtype=torch.uint8, device=data.device)
+        _lib.check(lib.rua_segment_reduce_gather(_ptr(data), row_index.data_ptr(), off.data_ptr(), N, S, H, dt, op,
+                                                 out.data_ptr(), ws.data_ptr(), nbytes, _stream()),
+                   'rua_segment_reduce_gather')
+    return out
+
+
+class _ScatterReduce(torch.autograd.Function):
+    """out[m] = reduce over {source[k] : index[k] == m}; rows of `source` are gathered in sorted-index order
+    inside the kernel.  Backward: gather the rows into sorted order, run the segment-reduce backward kernel,
+    scatter the gradient rows back -- every row is touched by exactly one thread, no atomics."""
+
+    @staticmethod
+    def forward(ctx, source: Tensor, srt: Tensor, off: Tensor, S: int, op: int):
+        flat = source.detach()
+        if not flat.is_contiguous():
+            flat = flat.contiguous()
+        out = _reduce_gather_raw(flat, srt, off, S, op)
+        ctx.op, ctx.S = op, S
+        ctx.save_for_backward(flat, srt, off, out)
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_out: Tensor):
+        lib = _lib.load()
+        source, srt, off, out = ctx.saved_tensors
+        g = grad_out.contiguous()
+        K = srt.numel()
+        H = source[0].numel() if source.shape[0] else 0
+        grad = torch.zeros_like(source)
+        if K > 0 and H > 0:
+            ordered = _GatherRows.apply(source, srt)              # rows in sorted-index order
+            grad_ordered = torch.empty_like(ordered)
+            dt = _DTYPES[source.dtype]
+            with _on(source.device):
+                nbytes = lib.rua_segment_reduce_backward_workspace_bytes(K, ctx.S, H, dt, ctx.op)
+                ws = torch.empty(max(nbytes, 16), dtype=torch.uint8, device=source.device)
+                _lib.check(lib.rua_segment_reduce_backward(g.data_ptr(), out.data_ptr(), ordered.data_ptr(),
+                                                           off.data_ptr(), K, ctx.S, H, dt, ctx.op,
+                                                           grad_ordered.data_ptr(), ws.data_ptr(), nbytes, _stream()),
+                           'rua_segment_reduce_backward')
+            scatter_rows_(grad, srt, grad_ordered)
+        return grad, None, None, None, None
+
+
+def scatter_reduce(source: Tensor, index: Tensor, buckets: int, op: str):
+    """(reduced (buckets, *feat), counts (buckets,)) of `source` rows grouped by `index` along dim 0."""
+    require_cuda(source, index)
+    srt, _ = sort_keys(index, buckets - 1)
+    off = bucket_offsets(index, srt, buckets)
+    if source.requires_grad and torch.is_grad_enabled():
+        red = _ScatterReduce.apply(source, srt, off, buckets, _OPS[op])
+    else:
+        red = _reduce_gather_raw(source if source.is_contiguous() else source.contiguous(), srt, off, buckets, _OPS[op])
+    return red, off[1:] - off[:-1]

@@ -1,31 +1,42 @@
-"""compose(list of ragged batches) -> one PackedSequence of sequences-of-sequences; mirror of
-torchrua/compose.py:9-33.  Outside the (a)-(e) hot path: a composition of
-idx / cat / pack / invert_permutation / gather, all of which are native here."""
+"""compose(batches) -> one PackedSequence holding every sequence of every batch (mirror of
+torchrua/compose.py:9-33; outside the (a)-(e) hot path).
+
+Two nested packings, both done by the native kernels:
+  * INNER: all sequences of all batches, taken as one ragged batch of flat storage rows, are packed
+    (stable descending device sort, one row-map launch over the int64 row indices);
+  * OUTER: the per-batch sequence counts are packed too, which yields the order in which a consumer
+    (e.g. an RNN over "sequences of sequences") wants the sequences back.
+The result's unsorted_indices is the composition of the two permutations; the payload is gathered once.
+"""
 from typing import List
 
 import torch
 
+from torchrua_b200 import _native
 from torchrua_b200.layout import C, P, Z
-from torchrua_b200.utils import invert_permutation
 
 
 def compose(sequences: List[Z]) -> P:
-    offset, data, indices, token_sizes = 0, [], [], []
-    for sequence in sequences:
-        raw = sequence.raw()
-        data.append(raw)
-        idx, sizes = sequence.idx().cat()
-        indices.append(idx + offset)
-        token_sizes.append(sizes)
-        offset += raw.size()[0]
+    payloads, row_ids, lengths, base = [], [], [], 0
+    for z in sequences:
+        flat = z.raw()
+        cat_rows = z.idx().cat()                      # storage row of every token, sequence-major
+        payloads.append(flat)
+        row_ids.append(cat_rows.data + base)
+        lengths.append(cat_rows.token_sizes)
+        base += flat.size()[0]
 
-    token_sizes = C.new(token_sizes)
-    unsorted_indices = token_sizes.idx().pack().data
+    all_lengths = torch.cat(lengths, dim=0)
+    counts = torch.tensor([n.size()[0] for n in lengths], dtype=torch.long, device=all_lengths.device)
 
-    indices = C(data=torch.cat(indices, dim=0), token_sizes=token_sizes.data).pack()
-    unsorted_indices = indices.unsorted_indices[unsorted_indices]
-    indices = indices._replace(
-        sorted_indices=invert_permutation(unsorted_indices),
+    outer = C(data=torch.arange(all_lengths.size()[0], dtype=torch.long, device=all_lengths.device),
+              token_sizes=counts).pack()
+    inner = C(data=torch.cat(row_ids, dim=0), token_sizes=all_lengths).pack()
+
+    unsorted_indices = inner.unsorted_indices[outer.data]
+    return P(
+        data=_native.gather_rows(torch.cat(payloads, dim=0), inner.data),
+        batch_sizes=inner.batch_sizes,
+        sorted_indices=_native.invert_permutation(unsorted_indices),
         unsorted_indices=unsorted_indices,
     )
-    return torch.cat(data, dim=0)[indices]

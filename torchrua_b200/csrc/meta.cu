@@ -149,12 +149,13 @@ constexpr int kSortTile = kSortThreads * kSortRounds;  // 2048 elements per CTA
 constexpr int kRadix = 256;
 
 struct SortSrc {
-  const int64_t* len;     // pass 0: key = T - len[i], val = i
+  const int64_t* len;     // pass 0: key = T - len[i] (descending sort) or len[i] (ascending), val = i
   const uint32_t* keys;   // later passes
   const uint32_t* vals;
   int64_t T;
+  int ascending;
   __device__ __forceinline__ void load(int64_t i, uint32_t& k, uint32_t& v) const {
-    if (len) { k = (uint32_t)(T - len[i]); v = (uint32_t)i; }
+    if (len) { k = ascending ? (uint32_t)len[i] : (uint32_t)(T - len[i]); v = (uint32_t)i; }
     else { k = keys[i]; v = vals[i]; }
   }
 };
@@ -295,6 +296,19 @@ __global__ void lengths_from_pack_kernel(const int64_t* __restrict__ bs, const i
   len[i] = lo;
 }
 
+// off[m] = first rank r with keys[sorted[r]] >= m  (keys o sorted is non-decreasing), m in [0, M]
+__global__ void bucket_offsets_kernel(const int64_t* __restrict__ keys, const int64_t* __restrict__ sorted,
+                                      int64_t n, int64_t M, int64_t* __restrict__ off) {
+  int64_t m = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (m > M) return;
+  int64_t lo = 0, hi = n;
+  while (lo < hi) {
+    int64_t mid = (lo + hi) >> 1;
+    if (__ldg(keys + __ldg(sorted + mid)) < m) lo = mid + 1; else hi = mid;
+  }
+  off[m] = lo;
+}
+
 }  // namespace rua
 
 using namespace rua;
@@ -357,7 +371,20 @@ size_t rua_sort_workspace_bytes(int64_t B) {
   return (size_t)(4 * B + (int64_t)kRadix * nblk) * sizeof(uint32_t) + 64;
 }
 
+static int sort_impl(const int64_t* len, int64_t B, int64_t T, int ascending, int64_t* sorted, int64_t* unsorted,
+                     void* ws, size_t ws_bytes, rua_stream_t stream);
+
 int rua_sort_lengths(const int64_t* len, int64_t B, int64_t T, int64_t* sorted, int64_t* unsorted,
+                     void* ws, size_t ws_bytes, rua_stream_t stream) {
+  return sort_impl(len, B, T, 0, sorted, unsorted, ws, ws_bytes, stream);
+}
+
+int rua_sort_keys(const int64_t* keys, int64_t n, int64_t max_key, int64_t* sorted, int64_t* unsorted,
+                  void* ws, size_t ws_bytes, rua_stream_t stream) {
+  return sort_impl(keys, n, max_key, 1, sorted, unsorted, ws, ws_bytes, stream);
+}
+
+static int sort_impl(const int64_t* len, int64_t B, int64_t T, int ascending, int64_t* sorted, int64_t* unsorted,
                      void* ws, size_t ws_bytes, rua_stream_t stream) {
   if (B < 0 || T < 0) return RUA_ERR_INVALID;
   if (B == 0) return RUA_OK;
@@ -377,6 +404,7 @@ int rua_sort_lengths(const int64_t* len, int64_t B, int64_t T, int64_t* sorted, 
   for (int p = 0; p < passes; ++p) {
     SortSrc src;
     src.T = T;
+    src.ascending = ascending;
     if (p == 0) { src.len = len; src.keys = nullptr; src.vals = nullptr; }
     else { src.len = nullptr; src.keys = keys[(p - 1) & 1]; src.vals = vals[(p - 1) & 1]; }
     int shift = 8 * p;
@@ -409,6 +437,14 @@ int rua_batch_sizes(const int64_t* len, const int64_t* sorted, int64_t B, int64_
   if (T == 0) return RUA_OK;
   if (!len || !sorted || !bs) return RUA_ERR_INVALID;
   batch_sizes_kernel<<<(unsigned)ceil_div(T, 256), 256, 0, (cudaStream_t)stream>>>(len, sorted, B, T, bs);
+  return check_launch();
+}
+
+int rua_bucket_offsets(const int64_t* keys, const int64_t* sorted, int64_t n, int64_t M, int64_t* off,
+                       rua_stream_t stream) {
+  if (n < 0 || M < 0 || !off) return RUA_ERR_INVALID;
+  if (n > 0 && (!keys || !sorted)) return RUA_ERR_INVALID;
+  bucket_offsets_kernel<<<(unsigned)ceil_div(M + 1, 256), 256, 0, (cudaStream_t)stream>>>(keys, sorted, n, M, off);
   return check_launch();
 }
 

@@ -26,17 +26,17 @@ namespace rua {
 // narrow rows (H * elem <= 16 bytes) run on the rows-on-lanes kernels of reduce_flat.cu
 bool flat_supported(int32_t dtype, int64_t H);
 int flat_rows_per_tile(int32_t dtype, int64_t H);
-int flat_launch(int32_t dtype, int64_t H, int32_t op, const void* data, const int64_t* off, int64_t N, int64_t S,
-                void* out, void* head, void* tail, int64_t* tail_seg, void* hdr, int vector_loads, int64_t tiles,
-                cudaStream_t st);
+int flat_launch(int32_t dtype, int64_t H, int32_t op, const void* data, const int64_t* ridx, const int64_t* off,
+                int64_t N, int64_t S, void* out, void* head, void* tail, int64_t* tail_seg, void* hdr,
+                int vector_loads, int64_t tiles, cudaStream_t st);
 
 // ---------------------------------------------------------------------------------------------
 // main kernel
 // ---------------------------------------------------------------------------------------------
 template <typename T, int V, int OP>
 __global__ void __launch_bounds__(kRedThreads, Store<T>::kMinBlocks)
-segreduce_kernel(const T* __restrict__ data, const int64_t* __restrict__ off, int64_t N, int64_t S, int64_t H,
-                 int R, T* __restrict__ out, typename Store<T>::Acc* __restrict__ head,
+segreduce_kernel(const T* __restrict__ data, const int64_t* __restrict__ ridx, const int64_t* __restrict__ off,
+                 int64_t N, int64_t S, int64_t H, int R, T* __restrict__ out, typename Store<T>::Acc* __restrict__ head,
                  typename Store<T>::Acc* __restrict__ tail, int64_t* __restrict__ tail_seg, RedHeader* hdr) {
   using A = typename Store<T>::Acc;
   constexpr bool kFast = sizeof(T) == 2;  // 16-bit storage: 1e-2 tolerance, approximate exp is plenty
@@ -65,7 +65,7 @@ segreduce_kernel(const T* __restrict__ data, const int64_t* __restrict__ off, in
     if (active) {
 #pragma unroll
       for (int k = 0; k < kRedUnroll; ++k)
-        if (r + k < row1) load_raw<T, V>(colp + (r + k) * H, raw[k]);
+        if (r + k < row1) load_raw<T, V>(colp + (ridx ? __ldg(ridx + r + k) : r + k) * H, raw[k]);  // optional row gather
     }
     // the current segment ends after row `seg_end - 1`: store it and move to the next non-empty one
     auto finish_segment = [&]() {
@@ -273,8 +273,8 @@ static RedPlan plan_reduce(int64_t N, int64_t H, int32_t dtype, int32_t op, cons
 }
 
 template <typename T, int V, int OP>
-static int run_reduce(const RedPlan& p, const void* data, const int64_t* off, int64_t N, int64_t S, int64_t H,
-                      void* out, void* ws, cudaStream_t st) {
+static int run_reduce(const RedPlan& p, const void* data, const int64_t* ridx, const int64_t* off, int64_t N, int64_t S,
+                      int64_t H, void* out, void* ws, cudaStream_t st) {
   using A = typename Store<T>::Acc;
   RedHeader* hdr = (RedHeader*)ws;
   int64_t* tail_seg = (int64_t*)((char*)ws + sizeof(RedHeader));
@@ -289,10 +289,10 @@ static int run_reduce(const RedPlan& p, const void* data, const int64_t* off, in
     if (p.col_tiles > 65535) return RUA_ERR_UNSUPPORTED;
     dim3 grid((unsigned)p.chunks, (unsigned)p.col_tiles);
     if (p.flat) {
-      rc = flat_launch(p.dtype, H, OP, data, off, N, S, out, head, tail, tail_seg, hdr, p.vector_loads, p.chunks, st);
+      rc = flat_launch(p.dtype, H, OP, data, ridx, off, N, S, out, head, tail, tail_seg, hdr, p.vector_loads && !ridx, p.chunks, st);
       if (rc) return rc;
     } else {
-      segreduce_kernel<T, V, OP><<<grid, p.threads, 0, st>>>((const T*)data, off, N, S, H, p.R, (T*)out, head, tail, tail_seg, hdr);
+      segreduce_kernel<T, V, OP><<<grid, p.threads, 0, st>>>((const T*)data, ridx, off, N, S, H, p.R, (T*)out, head, tail, tail_seg, hdr);
       if ((rc = check_launch())) return rc;
     }
     if (p.chunks > 1) {
@@ -307,24 +307,24 @@ static int run_reduce(const RedPlan& p, const void* data, const int64_t* off, in
 }
 
 template <typename T, int V>
-static int dispatch_op(int32_t op, const RedPlan& p, const void* data, const int64_t* off, int64_t N, int64_t S,
-                       int64_t H, void* out, void* ws, cudaStream_t st) {
+static int dispatch_op(int32_t op, const RedPlan& p, const void* data, const int64_t* ridx, const int64_t* off, int64_t N,
+                       int64_t S, int64_t H, void* out, void* ws, cudaStream_t st) {
   switch (op) {
-    case RUA_SUM: return run_reduce<T, V, RUA_SUM>(p, data, off, N, S, H, out, ws, st);
-    case RUA_MEAN: return run_reduce<T, V, RUA_MEAN>(p, data, off, N, S, H, out, ws, st);
-    case RUA_PROD: return run_reduce<T, V, RUA_PROD>(p, data, off, N, S, H, out, ws, st);
-    case RUA_MAX: return run_reduce<T, V, RUA_MAX>(p, data, off, N, S, H, out, ws, st);
-    case RUA_MIN: return run_reduce<T, V, RUA_MIN>(p, data, off, N, S, H, out, ws, st);
-    case RUA_LOGSUMEXP: return run_reduce<T, V, RUA_LOGSUMEXP>(p, data, off, N, S, H, out, ws, st);
+    case RUA_SUM: return run_reduce<T, V, RUA_SUM>(p, data, ridx, off, N, S, H, out, ws, st);
+    case RUA_MEAN: return run_reduce<T, V, RUA_MEAN>(p, data, ridx, off, N, S, H, out, ws, st);
+    case RUA_PROD: return run_reduce<T, V, RUA_PROD>(p, data, ridx, off, N, S, H, out, ws, st);
+    case RUA_MAX: return run_reduce<T, V, RUA_MAX>(p, data, ridx, off, N, S, H, out, ws, st);
+    case RUA_MIN: return run_reduce<T, V, RUA_MIN>(p, data, ridx, off, N, S, H, out, ws, st);
+    case RUA_LOGSUMEXP: return run_reduce<T, V, RUA_LOGSUMEXP>(p, data, ridx, off, N, S, H, out, ws, st);
     default: return RUA_ERR_INVALID;
   }
 }
 
 template <typename T>
-static int dispatch_vec(int32_t op, const RedPlan& p, const void* data, const int64_t* off, int64_t N, int64_t S,
-                        int64_t H, void* out, void* ws, cudaStream_t st) {
-  if (p.vec == 1) return dispatch_op<T, 1>(op, p, data, off, N, S, H, out, ws, st);
-  return dispatch_op<T, Store<T>::kVec>(op, p, data, off, N, S, H, out, ws, st);
+static int dispatch_vec(int32_t op, const RedPlan& p, const void* data, const int64_t* ridx, const int64_t* off, int64_t N,
+                        int64_t S, int64_t H, void* out, void* ws, cudaStream_t st) {
+  if (p.vec == 1) return dispatch_op<T, 1>(op, p, data, ridx, off, N, S, H, out, ws, st);
+  return dispatch_op<T, Store<T>::kVec>(op, p, data, ridx, off, N, S, H, out, ws, st);
 }
 
 }  // namespace rua
@@ -346,6 +346,13 @@ size_t rua_segment_reduce_workspace_bytes(int64_t N, int64_t S, int64_t H, int32
 
 int rua_segment_reduce(const void* data, const int64_t* off, int64_t N, int64_t S, int64_t H, int32_t dtype,
                        int32_t op, void* out, void* ws, size_t ws_bytes, rua_stream_t stream) {
+  return rua_segment_reduce_gather(data, nullptr, off, N, S, H, dtype, op, out, ws, ws_bytes, stream);
+}
+
+int rua_segment_reduce_gather(const void* data, const int64_t* row_index, const int64_t* off, int64_t N, int64_t S,
+                              int64_t H, int32_t dtype, int32_t op, void* out, void* ws, size_t ws_bytes,
+                              rua_stream_t stream) {
+  const int64_t* ridx = row_index;
   if (N < 0 || S < 0 || H < 0) return RUA_ERR_INVALID;
   if (S == 0 || H == 0) return RUA_OK;
   if (!off || !out || !ws || (N > 0 && !data)) return RUA_ERR_INVALID;
@@ -357,10 +364,10 @@ int rua_segment_reduce(const void* data, const int64_t* off, int64_t N, int64_t 
   if (((uintptr_t)ws & 15u) != 0) return RUA_ERR_INVALID;
   cudaStream_t st = (cudaStream_t)stream;
   switch (dtype) {
-    case RUA_F32: return dispatch_vec<float>(op, p, data, off, N, S, H, out, ws, st);
-    case RUA_F64: return dispatch_vec<double>(op, p, data, off, N, S, H, out, ws, st);
-    case RUA_F16: return dispatch_vec<__half>(op, p, data, off, N, S, H, out, ws, st);
-    default: return dispatch_vec<__nv_bfloat16>(op, p, data, off, N, S, H, out, ws, st);
+    case RUA_F32: return dispatch_vec<float>(op, p, data, ridx, off, N, S, H, out, ws, st);
+    case RUA_F64: return dispatch_vec<double>(op, p, data, ridx, off, N, S, H, out, ws, st);
+    case RUA_F16: return dispatch_vec<__half>(op, p, data, ridx, off, N, S, H, out, ws, st);
+    default: return dispatch_vec<__nv_bfloat16>(op, p, data, ridx, off, N, S, H, out, ws, st);
   }
 }
 

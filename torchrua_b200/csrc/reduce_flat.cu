@@ -40,7 +40,8 @@ __device__ __forceinline__ State<A, HE, OP> flat_shfl_up(const State<A, HE, OP>&
 
 template <typename T, int HE, int OP>
 __global__ void __launch_bounds__(kFlatThreads)
-segreduce_flat_kernel(const T* __restrict__ data, const int64_t* __restrict__ off, int64_t N, int64_t S,
+segreduce_flat_kernel(const T* __restrict__ data, const int64_t* __restrict__ ridx, const int64_t* __restrict__ off,
+                      int64_t N, int64_t S,
                       T* __restrict__ out, typename Store<T>::Acc* __restrict__ head,
                       typename Store<T>::Acc* __restrict__ tail, int64_t* __restrict__ tail_seg, RedHeader* hdr,
                       int vector_loads) {
@@ -99,7 +100,10 @@ segreduce_flat_kernel(const T* __restrict__ data, const int64_t* __restrict__ of
     Store<T>::unpack(raw, x);
   } else {
 #pragma unroll
-    for (int k = 0; k < E; ++k) x[k] = tr0 + k / HE < nrows ? Store<T>::to_acc(data[(row0 + tr0) * HE + k]) : A(0);
+    for (int k = 0; k < E; ++k) {
+      const int64_t row = row0 + tr0 + k / HE;                       // optional row gather (scatter_*)
+      x[k] = tr0 + k / HE < nrows ? Store<T>::to_acc(data[(ridx ? __ldg(ridx + row) : row) * HE + k % HE]) : A(0);
+    }
   }
 
   A ext = OP == RUA_MIN ? -inf_of<A>() : inf_of<A>();
@@ -286,37 +290,37 @@ segreduce_flat_kernel(const T* __restrict__ data, const int64_t* __restrict__ of
 }
 
 template <typename T, int HE, int OP>
-static void flat_launch3(const void* data, const int64_t* off, int64_t N, int64_t S, void* out, void* head, void* tail,
+static void flat_launch3(const void* data, const int64_t* ridx, const int64_t* off, int64_t N, int64_t S, void* out, void* head, void* tail,
                          int64_t* tail_seg, RedHeader* hdr, int vector_loads, int64_t tiles, cudaStream_t st) {
   using A = typename Store<T>::Acc;
   segreduce_flat_kernel<T, HE, OP><<<(unsigned)tiles, kFlatThreads, 0, st>>>(
-      (const T*)data, off, N, S, (T*)out, (A*)head, (A*)tail, tail_seg, hdr, vector_loads);
+      (const T*)data, ridx, off, N, S, (T*)out, (A*)head, (A*)tail, tail_seg, hdr, vector_loads);
 }
 
 template <typename T, int HE>
-static int flat_launch2(int op, const void* data, const int64_t* off, int64_t N, int64_t S, void* out, void* head,
+static int flat_launch2(int op, const void* data, const int64_t* ridx, const int64_t* off, int64_t N, int64_t S, void* out, void* head,
                         void* tail, int64_t* tail_seg, RedHeader* hdr, int vl, int64_t tiles, cudaStream_t st) {
   switch (op) {
-    case RUA_SUM: flat_launch3<T, HE, RUA_SUM>(data, off, N, S, out, head, tail, tail_seg, hdr, vl, tiles, st); break;
-    case RUA_MEAN: flat_launch3<T, HE, RUA_MEAN>(data, off, N, S, out, head, tail, tail_seg, hdr, vl, tiles, st); break;
-    case RUA_PROD: flat_launch3<T, HE, RUA_PROD>(data, off, N, S, out, head, tail, tail_seg, hdr, vl, tiles, st); break;
-    case RUA_MAX: flat_launch3<T, HE, RUA_MAX>(data, off, N, S, out, head, tail, tail_seg, hdr, vl, tiles, st); break;
-    case RUA_MIN: flat_launch3<T, HE, RUA_MIN>(data, off, N, S, out, head, tail, tail_seg, hdr, vl, tiles, st); break;
-    case RUA_LOGSUMEXP: flat_launch3<T, HE, RUA_LOGSUMEXP>(data, off, N, S, out, head, tail, tail_seg, hdr, vl, tiles, st); break;
+    case RUA_SUM: flat_launch3<T, HE, RUA_SUM>(data, ridx, off, N, S, out, head, tail, tail_seg, hdr, vl, tiles, st); break;
+    case RUA_MEAN: flat_launch3<T, HE, RUA_MEAN>(data, ridx, off, N, S, out, head, tail, tail_seg, hdr, vl, tiles, st); break;
+    case RUA_PROD: flat_launch3<T, HE, RUA_PROD>(data, ridx, off, N, S, out, head, tail, tail_seg, hdr, vl, tiles, st); break;
+    case RUA_MAX: flat_launch3<T, HE, RUA_MAX>(data, ridx, off, N, S, out, head, tail, tail_seg, hdr, vl, tiles, st); break;
+    case RUA_MIN: flat_launch3<T, HE, RUA_MIN>(data, ridx, off, N, S, out, head, tail, tail_seg, hdr, vl, tiles, st); break;
+    case RUA_LOGSUMEXP: flat_launch3<T, HE, RUA_LOGSUMEXP>(data, ridx, off, N, S, out, head, tail, tail_seg, hdr, vl, tiles, st); break;
     default: return RUA_ERR_INVALID;
   }
   return check_launch();
 }
 
 template <typename T>
-static int flat_launch1(int he, int op, const void* data, const int64_t* off, int64_t N, int64_t S, void* out,
+static int flat_launch1(int he, int op, const void* data, const int64_t* ridx, const int64_t* off, int64_t N, int64_t S, void* out,
                         void* head, void* tail, int64_t* tail_seg, RedHeader* hdr, int vl, int64_t tiles,
                         cudaStream_t st) {
   constexpr int E = 16 / sizeof(T);
-  if (he == 1) return flat_launch2<T, 1>(op, data, off, N, S, out, head, tail, tail_seg, hdr, vl, tiles, st);
-  if constexpr (E >= 2) if (he == 2) return flat_launch2<T, 2>(op, data, off, N, S, out, head, tail, tail_seg, hdr, vl, tiles, st);
-  if constexpr (E >= 4) if (he == 4) return flat_launch2<T, 4>(op, data, off, N, S, out, head, tail, tail_seg, hdr, vl, tiles, st);
-  if constexpr (E >= 8) if (he == 8) return flat_launch2<T, 8>(op, data, off, N, S, out, head, tail, tail_seg, hdr, vl, tiles, st);
+  if (he == 1) return flat_launch2<T, 1>(op, data, ridx, off, N, S, out, head, tail, tail_seg, hdr, vl, tiles, st);
+  if constexpr (E >= 2) if (he == 2) return flat_launch2<T, 2>(op, data, ridx, off, N, S, out, head, tail, tail_seg, hdr, vl, tiles, st);
+  if constexpr (E >= 4) if (he == 4) return flat_launch2<T, 4>(op, data, ridx, off, N, S, out, head, tail, tail_seg, hdr, vl, tiles, st);
+  if constexpr (E >= 8) if (he == 8) return flat_launch2<T, 8>(op, data, ridx, off, N, S, out, head, tail, tail_seg, hdr, vl, tiles, st);
   return RUA_ERR_UNSUPPORTED;
 }
 
@@ -331,15 +335,15 @@ int flat_rows_per_tile(int32_t dtype, int64_t H) {
   return kFlatThreads * (e / (int)H);
 }
 
-int flat_launch(int32_t dtype, int64_t H, int32_t op, const void* data, const int64_t* off, int64_t N, int64_t S,
-                void* out, void* head, void* tail, int64_t* tail_seg, void* hdr, int vector_loads, int64_t tiles,
-                cudaStream_t st) {
+int flat_launch(int32_t dtype, int64_t H, int32_t op, const void* data, const int64_t* ridx, const int64_t* off,
+                int64_t N, int64_t S, void* out, void* head, void* tail, int64_t* tail_seg, void* hdr,
+                int vector_loads, int64_t tiles, cudaStream_t st) {
   RedHeader* h = (RedHeader*)hdr;
   switch (dtype) {
-    case RUA_F32: return flat_launch1<float>((int)H, op, data, off, N, S, out, head, tail, tail_seg, h, vector_loads, tiles, st);
-    case RUA_F64: return flat_launch1<double>((int)H, op, data, off, N, S, out, head, tail, tail_seg, h, vector_loads, tiles, st);
-    case RUA_F16: return flat_launch1<__half>((int)H, op, data, off, N, S, out, head, tail, tail_seg, h, vector_loads, tiles, st);
-    default: return flat_launch1<__nv_bfloat16>((int)H, op, data, off, N, S, out, head, tail, tail_seg, h, vector_loads, tiles, st);
+    case RUA_F32: return flat_launch1<float>((int)H, op, data, ridx, off, N, S, out, head, tail, tail_seg, h, vector_loads, tiles, st);
+    case RUA_F64: return flat_launch1<double>((int)H, op, data, ridx, off, N, S, out, head, tail, tail_seg, h, vector_loads, tiles, st);
+    case RUA_F16: return flat_launch1<__half>((int)H, op, data, ridx, off, N, S, out, head, tail, tail_seg, h, vector_loads, tiles, st);
+    default: return flat_launch1<__nv_bfloat16>((int)H, op, data, ridx, off, N, S, out, head, tail, tail_seg, h, vector_loads, tiles, st);
   }
 }
 

@@ -2,8 +2,8 @@
 
 segment_* (reduce.py:34-69) run on the native segment-reduce kernel (rua_segment_reduce): one pass
 over the data with fp32 accumulation, logsumexp fused, the reference's `initial` quirks reproduced
-without the extra global-min pass.  scatter_* (reduce.py:6-31) are outside the hot path (unsorted
-index reductions, SURVEY.md 8f "next" row 1) and still compose ATen ops exactly like the reference.
+without the extra global-min pass.  scatter_* (reduce.py:6-31; SURVEY.md 8f "next" row 1) sort the
+index on the device and run the same kernel over gathered rows instead of ATen's atomics.
 """
 import torch
 
@@ -13,32 +13,64 @@ from torchrua_b200._native import MapSpec, SideSpec
 from torchrua_b200.layout import T
 
 
-def scatter_max(tensor: T, index: T, source: T, include_self: bool = False, dim: int = 0):
-    return torch.index_reduce(tensor, index=index, source=source, reduce='amax', include_self=include_self, dim=dim)
+_FLOATS = (torch.float16, torch.bfloat16, torch.float32, torch.float64)
 
 
-def scatter_min(tensor: T, index: T, source: T, include_self: bool = False, dim: int = 0):
-    return torch.index_reduce(tensor, index=index, source=source, reduce='amin', include_self=include_self, dim=dim)
+def _scatter(tensor: T, index: T, source: T, include_self: bool, dim: int, op: str) -> T:
+    """out[m] = op over {source[k] : index[k] == m} (and tensor[m] if include_self); rows no index points at
+    keep tensor[m] (index_reduce semantics, reduce.py:6-23) -- except for `sum`, whose reference goes through
+    index_add on zeros (reduce.py:14-15).
+
+    Native path: stable device sort of `index`, bucket boundaries, then ONE segment-reduce launch that gathers
+    the source rows in sorted order inside the kernel (rua_segment_reduce_gather).  Deterministic: no atomics.
+    The O(M) combination with `tensor` is elementwise torch code, which also gives its gradient."""
+    if dim != 0:
+        out = _scatter(tensor.movedim(dim, 0), index, source.movedim(dim, 0), include_self, 0, op)
+        return out.movedim(0, dim)
+    native = 'sum' if op == 'mean' else op
+    reduced, count = _native.scatter_reduce(source, index, tensor.size()[0], native)
+    shape = (-1,) + (1,) * (tensor.dim() - 1)
+    touched = (count > 0).view(shape)
+    if op == 'sum':
+        return tensor + reduced if include_self else reduced
+    if op == 'mean':
+        denom = (count + int(include_self)).clamp_min(1).to(dtype=tensor.dtype).view(shape)
+        total = reduced + tensor if include_self else reduced
+        return torch.where(touched, total / denom, tensor)
+    if op == 'prod':
+        return torch.where(touched, reduced * tensor if include_self else reduced, tensor)
+    if op == 'max':
+        return torch.where(touched, torch.maximum(reduced, tensor) if include_self else reduced, tensor)
+    if op == 'min':
+        return torch.where(touched, torch.minimum(reduced, tensor) if include_self else reduced, tensor)
+    # logsumexp (reduce.py:26-31): untouched rows give log(exp(0)) + tensor with include_self, log(0) without
+    if include_self:
+        return torch.where(touched, torch.logaddexp(reduced, tensor), tensor)
+    return torch.where(touched, reduced, torch.full_like(reduced, float('-inf')))
 
 
-def scatter_sum(tensor: T, index: T, source: T, include_self: bool = False, dim: int = 0):
-    base = tensor if include_self else torch.zeros_like(tensor)
-    return torch.index_add(base, index=index, source=source, dim=dim)
+def _scatter_aten(tensor, index, source, include_self, dim, reduce):
+    # integer payloads: the native reduction kernels are floating point only (like segment_reduce)
+    if reduce == 'sum':
+        return torch.index_add(tensor if include_self else torch.zeros_like(tensor), index=index, source=source, dim=dim)
+    return torch.index_reduce(tensor, index=index, source=source, reduce=reduce, include_self=include_self, dim=dim)
 
 
-def scatter_mean(tensor: T, index: T, source: T, include_self: bool = False, dim: int = 0):
-    return torch.index_reduce(tensor, index=index, source=source, reduce='mean', include_self=include_self, dim=dim)
+def _scatter_dispatch(op, aten_name):
+    def scatter(tensor: T, index: T, source: T, include_self: bool = False, dim: int = 0):
+        if tensor.dtype in _FLOATS and source.dtype == tensor.dtype:
+            return _scatter(tensor, index, source, include_self, dim, op)
+        return _scatter_aten(tensor, index, source, include_self, dim, aten_name)
+    scatter.__name__ = 'scatter_' + op
+    return scatter
 
 
-def scatter_prod(tensor: T, index: T, source: T, include_self: bool = False, dim: int = 0):
-    return torch.index_reduce(tensor, index=index, source=source, reduce='prod', include_self=include_self, dim=dim)
-
-
-def scatter_logsumexp(tensor: T, index: T, source: T, include_self: bool = False, dim: int = 0):
-    m = scatter_max(tensor, index=index, source=source, include_self=include_self, dim=dim).detach()
-    shifted_self = (tensor - m).exp()
-    shifted_source = (source - m[index]).exp()
-    return scatter_sum(shifted_self, index=index, source=shifted_source, include_self=include_self, dim=dim).log() + m
+scatter_max = _scatter_dispatch('max', 'amax')
+scatter_min = _scatter_dispatch('min', 'amin')
+scatter_sum = _scatter_dispatch('sum', 'sum')
+scatter_mean = _scatter_dispatch('mean', 'mean')
+scatter_prod = _scatter_dispatch('prod', 'prod')
+scatter_logsumexp = _scatter_dispatch('logsumexp', None)
 
 
 def segment_max(tensor: T, segment_sizes: T) -> T:

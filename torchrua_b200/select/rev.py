@@ -5,13 +5,11 @@ from torchrua_b200.layout import C, L, P, R, Z
 from torchrua_b200.select._common import same_layout_map
 
 
-def rev(self: Z) -> Z:
+def cat_rev(self: Z) -> Z:
     return same_layout_map(self, MAP_REV)
 
 
-cat_rev = left_rev = pack_rev = right_rev = rev
+left_rev = pack_rev = right_rev = cat_rev   # one kernel serves all four layouts
 
-C.rev = rev
-L.rev = rev
-P.rev = rev
-R.rev = rev
+for _cls in (C, L, P, R):
+    _cls.rev = cat_rev

@@ -5,16 +5,14 @@ from torchrua_b200.layout import C, L, P, R, Z
 from torchrua_b200.select._common import same_layout_map
 
 
-def roll(self: Z, shifts: int) -> Z:
+def cat_roll(self: Z, shifts: int) -> Z:
     # L/R: the reference gathers through an index sequence padded with index 0, so padding slots of the
     # result hold flat row 0 of the input (roll.py:19-20,33-34); reproduced for bit-exactness
     padded = isinstance(self, (L, R))
     return same_layout_map(self, MAP_ROLL, int(shifts), PAD_ROW0 if padded else PAD_FILL)
 
 
-cat_roll = left_roll = pack_roll = right_roll = roll
+left_roll = pack_roll = right_roll = cat_roll   # one kernel serves all four layouts
 
-C.roll = roll
-L.roll = roll
-P.roll = roll
-R.roll = roll
+for _cls in (C, L, P, R):
+    _cls.roll = cat_roll

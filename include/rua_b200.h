@@ -222,6 +222,38 @@ int rua_segment_reduce_backward(const void* grad_out, const void* out, const voi
                                 int32_t op, void* grad_data, void* ws, size_t ws_bytes,
                                 rua_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------- */
+/* K5  multi-GPU output gather over NVLink peer memory (the reference is         */
+/* single-device).  One process per GPU; the batch is sharded by sequence; every rank stores its */
+/* rows directly into the output buffers ("windows") of all ranks of the node.                   */
+/* ------------------------------------------------------------------------------------------- */
+#define RUA_MAX_DESTINATIONS 16
+#define RUA_PEER_HANDLE_BYTES 64
+
+/* window = device allocation that other processes of the node can map (CUDA IPC).  alloc returns the
+ * local pointer and a 64-byte handle to ship to the peers; open maps a peer's window into this
+ * process (enables peer access lazily); close unmaps; free releases the local allocation.  These four
+ * calls synchronise the device (cudaMalloc / cudaFree semantics); they are set-up, not data path. */
+int rua_peer_window_alloc(size_t bytes, void** ptr, void* handle_host);
+int rua_peer_window_open(const void* handle_host, void** ptr);
+int rua_peer_window_close(void* ptr);
+int rua_peer_window_free(void* ptr);
+
+/* fused "local layout -> global C on every rank": the n_tokens tokens of the local shard are walked in cat
+ * order; token (i, t) is read ONCE from the local source layout (src_side: C, L, R or P over `ragged`) and
+ * stored at row dst_base_host[k][i] + t of destination k, for every k < n_dst <= RUA_MAX_DESTINATIONS.
+ * dst_base_host[k] is a DEVICE array of B int64 (first row of local sequence i in destination k), or NULL
+ * for "local cat row" (a contiguous local copy).  dst_host[k] are device pointers (local or peer windows);
+ * both arrays themselves live on the host.  Replaces to_cat (torchrua/core/cast.py:8-16) + all_gather. */
+int rua_row_map_multi(const void* src, int64_t row_bytes, const rua_ragged_t* ragged,
+                      const rua_side_t* src_side, int64_t n_tokens, void* const* dst_host,
+                      const int64_t* const* dst_base_host, int32_t n_dst, rua_stream_t stream);
+
+/* per-sequence results (segment reductions, last(), head(1)): row j of src (n, row_bytes) is stored at row
+ * index[j] of every destination. */
+int rua_scatter_rows_multi(const void* src, const int64_t* index, int64_t n, int64_t row_bytes,
+                           void* const* dst_host, int32_t n_dst, rua_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -62,7 +62,17 @@ SIGNATURES = {
     'rua_segment_reduce_backward_workspace_bytes': (c_size_t, [c_int64, c_int64, c_int64, c_int32, c_int32]),
     'rua_segment_reduce_backward': (c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int64,
                                               c_int32, c_int32, c_void_p, c_void_p, c_size_t, c_void_p]),
+    'rua_peer_window_alloc': (c_int32, [c_size_t, POINTER(c_void_p), c_char_p]),
+    'rua_peer_window_open': (c_int32, [c_char_p, POINTER(c_void_p)]),
+    'rua_peer_window_close': (c_int32, [c_void_p]),
+    'rua_peer_window_free': (c_int32, [c_void_p]),
+    'rua_row_map_multi': (c_int32, [c_void_p, c_int64, POINTER(Ragged), POINTER(Side), c_int64, POINTER(c_void_p),
+                                    POINTER(c_void_p), c_int32, c_void_p]),
+    'rua_scatter_rows_multi': (c_int32, [c_void_p, c_void_p, c_int64, c_int64, POINTER(c_void_p), c_int32, c_void_p]),
 }
+
+MAX_DESTINATIONS = 16      # RUA_MAX_DESTINATIONS
+PEER_HANDLE_BYTES = 64     # RUA_PEER_HANDLE_BYTES
 
 _lib = None
 

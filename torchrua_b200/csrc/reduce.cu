@@ -33,7 +33,7 @@ int flat_launch(int32_t dtype, int64_t H, int32_t op, const void* data, const in
 // ---------------------------------------------------------------------------------------------
 // main kernel
 // ---------------------------------------------------------------------------------------------
-template <typename T, int V, int OP>
+template <typename T, int V, int OP, bool GATHER>
 __global__ void __launch_bounds__(kRedThreads, Store<T>::kMinBlocks)
 segreduce_kernel(const T* __restrict__ data, const int64_t* __restrict__ ridx, const int64_t* __restrict__ off,
                  int64_t N, int64_t S, int64_t H, int R, T* __restrict__ out, typename Store<T>::Acc* __restrict__ head,
@@ -65,7 +65,7 @@ segreduce_kernel(const T* __restrict__ data, const int64_t* __restrict__ ridx, c
     if (active) {
 #pragma unroll
       for (int k = 0; k < kRedUnroll; ++k)
-        if (r + k < row1) load_raw<T, V>(colp + (ridx ? __ldg(ridx + r + k) : r + k) * H, raw[k]);  // optional row gather
+        if (r + k < row1) load_raw<T, V>(colp + (GATHER ? __ldg(ridx + r + k) : r + k) * H, raw[k]);  // compile-time: row gather (scatter_*)
     }
     // the current segment ends after row `seg_end - 1`: store it and move to the next non-empty one
     auto finish_segment = [&]() {
@@ -292,7 +292,10 @@ static int run_reduce(const RedPlan& p, const void* data, const int64_t* ridx, c
       rc = flat_launch(p.dtype, H, OP, data, ridx, off, N, S, out, head, tail, tail_seg, hdr, p.vector_loads && !ridx, p.chunks, st);
       if (rc) return rc;
     } else {
-      segreduce_kernel<T, V, OP><<<grid, p.threads, 0, st>>>((const T*)data, ridx, off, N, S, H, p.R, (T*)out, head, tail, tail_seg, hdr);
+      if (ridx)
+        segreduce_kernel<T, V, OP, true><<<grid, p.threads, 0, st>>>((const T*)data, ridx, off, N, S, H, p.R, (T*)out, head, tail, tail_seg, hdr);
+      else
+        segreduce_kernel<T, V, OP, false><<<grid, p.threads, 0, st>>>((const T*)data, ridx, off, N, S, H, p.R, (T*)out, head, tail, tail_seg, hdr);
       if ((rc = check_launch())) return rc;
     }
     if (p.chunks > 1) {

@@ -256,6 +256,91 @@ row_map_kernel(const RowMapParams p) {
 }
 
 // ------------------------------------------------------------------------------------------------
+// K5 -- fused conversion + output gather (multi-GPU).  The tokens of the LOCAL shard are
+// walked in cat order; token (i, t) is read once from the local source layout (C, L, R or P) and stored
+// to row base_k[i] + t of EVERY destination k: the windows of all peer GPUs (plain stores through NVLink
+// peer mappings: fire-and-forget, coalesced 32-byte sectors) and, optionally, a local contiguous copy
+// (base == NULL: row j).  One pass replaces "convert, all_gather padded shards, permute into global order".
+// With rows_are_sequences the source is a plain (n, *) matrix of per-sequence results (segment reductions,
+// last(), head(1)): row j goes to row base_k[j].
+// ------------------------------------------------------------------------------------------------
+constexpr int kMaxDst = RUA_MAX_DESTINATIONS;
+struct MultiDst {
+  uint8_t* dst[kMaxDst];
+  const int64_t* base[kMaxDst];
+  int32_t n;
+  int32_t rows_are_sequences;
+};
+
+template <typename V>
+__global__ void __launch_bounds__(kRowMapThreads)
+row_map_multi_kernel(const RowMapParams p, const MultiDst m) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = (int64_t)blockIdx.x * (kRowMapThreads / 32) + (threadIdx.x >> 5);
+  const int rpw = p.rows_per_warp;
+  const int64_t rows = p.d.rows;
+  const int64_t j0 = warp * rpw;
+  if (j0 >= rows) return;
+
+  int64_t srow = kNoRow, seq = 0, tok = 0;
+  {
+    const int64_t j = j0 + lane;
+    if (lane < rpw && j < rows) {
+      if (m.rows_are_sequences) {
+        srow = j; seq = j; tok = 0;
+      } else {
+        GlobalOff f{p.rg.off};
+        seq = owner_search(f, p.rg.B, j);
+        const int64_t o = f(seq);
+        tok = j - o;
+        srow = source_row(p, seq, tok, f(seq + 1) - o);
+      }
+    }
+  }
+  const int lpr = p.lanes_per_row;
+  const int groups = 32 / lpr;
+  const int g = lane / lpr, l = lane - g * lpr;
+  const int64_t cols_per = ceil_div(p.row_vecs, (int64_t)p.col_splits);
+  const int64_t c0 = (int64_t)blockIdx.y * cols_per;
+  const int64_t c1 = c0 + cols_per < p.row_vecs ? c0 + cols_per : p.row_vecs;
+  const V* __restrict__ src = reinterpret_cast<const V*>(p.src);
+  const int n = m.n;
+  const int k0 = (int)(warp % n);   // neighbouring warps start with different peers: all links busy at any instant
+
+  for (int r0 = 0; r0 < rpw; r0 += groups) {
+    const int r = r0 + g;
+    const int64_t s = shfl_i64(srow, r & 31);
+    const int64_t si = shfl_i64(seq, r & 31);
+    const int64_t st = shfl_i64(tok, r & 31);
+    if (r >= rpw || s < 0) continue;
+    const int64_t jl = j0 + r;      // local cat row
+    const V* srow_p = src + s * p.row_vecs;
+    constexpr int U = sizeof(V) >= 32 ? kUnroll / 2 : kUnroll;
+    int64_t c = c0 + l;
+    for (; c + (int64_t)(U - 1) * lpr < c1; c += (int64_t)U * lpr) {
+      V v[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) v[u] = ld_stream(srow_p + c + (int64_t)u * lpr);
+      for (int kk = 0; kk < n; ++kk) {
+        const int k = k0 + kk < n ? k0 + kk : k0 + kk - n;
+        const int64_t dj = m.base[k] ? __ldg(m.base[k] + si) + st : jl;
+        V* drow_p = reinterpret_cast<V*>(m.dst[k]) + dj * p.row_vecs;
+#pragma unroll
+        for (int u = 0; u < U; ++u) st_stream(drow_p + c + (int64_t)u * lpr, v[u]);
+      }
+    }
+    for (; c < c1; c += lpr) {
+      const V v = ld_stream(srow_p + c);
+      for (int kk = 0; kk < n; ++kk) {
+        const int k = k0 + kk < n ? k0 + kk : k0 + kk - n;
+        const int64_t dj = m.base[k] ? __ldg(m.base[k] + si) + st : jl;
+        st_stream(reinterpret_cast<V*>(m.dst[k]) + dj * p.row_vecs + c, v);
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 // narrow rows (< 128 bytes: token ids, indices, scalars -- BASELINE config 5).  A 20-step binary
 // search per 8-byte row would dominate, so here a CTA owns a TILE of consecutive destination
 // vectors: one warp-cooperative 32-ary search per tile end finds the segments (sequences or time
@@ -633,6 +718,38 @@ static int launch_row_map(RowMapParams& p, int64_t row_bytes, int64_t rows, cuda
   return check_launch();
 }
 
+static int launch_row_map_multi(RowMapParams& p, const MultiDst& m, int64_t row_bytes, int64_t rows, cudaStream_t st) {
+  if (rows <= 0 || row_bytes <= 0) return RUA_OK;
+  uintptr_t a = (uintptr_t)p.src | (uintptr_t)row_bytes;
+  for (int k = 0; k < m.n; ++k) a |= (uintptr_t)m.dst[k];
+  int vec = row_bytes >= 128 ? 32 : 16;
+  while (vec > 1 && (a & (uintptr_t)(vec - 1))) vec >>= 1;
+  p.row_vecs = row_bytes / vec;
+  int lpr = 1;
+  while (lpr < 32 && lpr < p.row_vecs) lpr <<= 1;
+  p.lanes_per_row = lpr;
+  const int64_t target_warps = (int64_t)kNumSMs * 32;
+  int rpw = 32;
+  while (rpw > 32 / lpr && rpw > 1 && ceil_div(rows, rpw) < target_warps) rpw >>= 1;
+  p.rows_per_warp = rpw;
+  const int64_t warps = ceil_div(rows, rpw);
+  int splits = 1;
+  while (warps * splits < target_warps && p.row_vecs / (splits * 2) >= 32 * kUnroll && splits < 64) splits *= 2;
+  p.col_splits = splits;
+  const int64_t blocks = ceil_div(warps, kRowMapThreads / 32);
+  if (blocks >= (1ll << 31)) return RUA_ERR_UNSUPPORTED;
+  dim3 grid((unsigned)blocks, (unsigned)splits);
+  switch (vec) {
+    case 32: row_map_multi_kernel<V256><<<grid, kRowMapThreads, 0, st>>>(p, m); break;
+    case 16: row_map_multi_kernel<uint4><<<grid, kRowMapThreads, 0, st>>>(p, m); break;
+    case 8: row_map_multi_kernel<uint2><<<grid, kRowMapThreads, 0, st>>>(p, m); break;
+    case 4: row_map_multi_kernel<unsigned int><<<grid, kRowMapThreads, 0, st>>>(p, m); break;
+    case 2: row_map_multi_kernel<unsigned short><<<grid, kRowMapThreads, 0, st>>>(p, m); break;
+    default: row_map_multi_kernel<unsigned char><<<grid, kRowMapThreads, 0, st>>>(p, m); break;
+  }
+  return check_launch();
+}
+
 static bool valid_side(const rua_side_t* s) {
   if (!s) return false;
   if (s->layout < RUA_CAT || s->layout > RUA_RIGHT) return false;
@@ -705,6 +822,53 @@ int rua_gather_rows(const void* src, int64_t src_rows, const int64_t* index, int
 int rua_scatter_rows(const void* src, const int64_t* index, int64_t n, int64_t row_bytes, void* dst,
                      int64_t dst_rows, rua_stream_t stream) {
   return index_rows(src, nullptr, index, n, dst_rows, row_bytes, dst, stream);
+}
+
+int rua_row_map_multi(const void* src, int64_t row_bytes, const rua_ragged_t* ragged, const rua_side_t* src_side,
+                      int64_t n_tokens, void* const* dst_host, const int64_t* const* dst_base_host, int32_t n_dst,
+                      rua_stream_t stream) {
+  if (!ragged || !valid_side(src_side) || row_bytes < 0 || n_tokens < 0) return RUA_ERR_INVALID;
+  if (n_dst < 0 || n_dst > kMaxDst) return RUA_ERR_INVALID;
+  if (n_tokens == 0 || row_bytes == 0 || n_dst == 0) return RUA_OK;
+  if (!src || !dst_host || !dst_base_host || !ragged->off || ragged->B <= 0) return RUA_ERR_INVALID;
+  if (src_side->len_xform != RUA_LEN_SAME) return RUA_ERR_INVALID;
+  if (src_side->layout == RUA_PACK && (!ragged->poff || !ragged->unsorted)) return RUA_ERR_INVALID;
+  RowMapParams p{};
+  p.src = (const uint8_t*)src;
+  p.rg = *ragged;
+  p.s = *src_side;
+  p.d.layout = RUA_CAT;
+  p.d.len_xform = RUA_LEN_SAME;
+  p.d.rows = n_tokens;
+  p.tmap = RUA_MAP_SHIFT;
+  p.pad_mode = RUA_PAD_FILL;
+  MultiDst m{};
+  m.n = n_dst;
+  for (int k = 0; k < n_dst; ++k) {
+    if (!dst_host[k]) return RUA_ERR_INVALID;
+    m.dst[k] = (uint8_t*)dst_host[k];
+    m.base[k] = dst_base_host[k];
+  }
+  return launch_row_map_multi(p, m, row_bytes, n_tokens, (cudaStream_t)stream);
+}
+
+int rua_scatter_rows_multi(const void* src, const int64_t* index, int64_t n, int64_t row_bytes,
+                           void* const* dst_host, int32_t n_dst, rua_stream_t stream) {
+  if (n < 0 || row_bytes < 0 || n_dst < 0 || n_dst > kMaxDst) return RUA_ERR_INVALID;
+  if (n == 0 || row_bytes == 0 || n_dst == 0) return RUA_OK;
+  if (!src || !index || !dst_host) return RUA_ERR_INVALID;
+  RowMapParams p{};
+  p.src = (const uint8_t*)src;
+  p.d.rows = n;
+  MultiDst m{};
+  m.n = n_dst;
+  m.rows_are_sequences = 1;
+  for (int k = 0; k < n_dst; ++k) {
+    if (!dst_host[k]) return RUA_ERR_INVALID;
+    m.dst[k] = (uint8_t*)dst_host[k];
+    m.base[k] = index;
+  }
+  return launch_row_map_multi(p, m, row_bytes, n, (cudaStream_t)stream);
 }
 
 }  // extern "C"

@@ -120,3 +120,162 @@ def gather_catted(local_data: Tensor, local_lengths: Tensor, parts: List[Tensor]
                                                           torch.repeat_interleave(loc_off, lens))
         result[dst] = out[r][:n]
     return result
+
+
+# ------------------------------------------------------------------------------------------------
+# exchange (2), B200-native: every rank's kernel stores its rows straight into the output buffers of all
+# ranks through NVLink peer mappings (K5, include/rua_b200.h).  No staging copy, no padding to the largest
+# shard, no permutation pass afterwards.  Host side = plumbing only: window set-up and a stream-ordered fence.
+# ------------------------------------------------------------------------------------------------
+class _DeviceMemory:
+    """adapter that lets torch wrap a raw device pointer without copying (``__cuda_array_interface__``)."""
+
+    def __init__(self, ptr: int, nbytes: int):
+        self.__cuda_array_interface__ = {'shape': (nbytes,), 'typestr': '|u1', 'data': (ptr, False), 'version': 2}
+
+
+class PeerWindows:
+    """one ``nbytes`` window per rank of ``group`` (all ranks on ONE node), each mapped into every process.
+
+    ``ptrs[r]`` is the address of rank r's window in THIS process; ``local`` is this rank's window as a
+    uint8 tensor.  Set-up synchronises (cudaMalloc + a host-side handle exchange); use it once and keep it.
+    """
+
+    def __init__(self, nbytes: int, group: Optional[dist.ProcessGroup] = None, device: Optional[torch.device] = None):
+        import ctypes
+
+        from torchrua_b200 import _lib
+        self._lib = _lib.load()
+        self.group = group
+        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        if self.world > _lib.MAX_DESTINATIONS - 1:
+            raise RuntimeError(f'torchrua_b200: at most {_lib.MAX_DESTINATIONS - 1} ranks per window group')
+        self.device = torch.device('cuda', torch.cuda.current_device()) if device is None else torch.device(device)
+        self.nbytes = (int(nbytes) + 255) // 256 * 256
+        with torch.cuda.device(self.device):
+            ptr, handle = ctypes.c_void_p(), ctypes.create_string_buffer(_lib.PEER_HANDLE_BYTES)
+            _lib.check(self._lib.rua_peer_window_alloc(self.nbytes, ctypes.byref(ptr), handle), 'rua_peer_window_alloc')
+            self._own = ptr.value
+            handles = [None] * self.world
+            dist.all_gather_object(handles, bytes(handle.raw), group=group)
+            self.ptrs, self._opened = [], []
+            for r, h in enumerate(handles):
+                if r == self.rank:
+                    self.ptrs.append(self._own)
+                    continue
+                peer = ctypes.c_void_p()
+                _lib.check(self._lib.rua_peer_window_open(h, ctypes.byref(peer)), 'rua_peer_window_open')
+                self.ptrs.append(peer.value)
+                self._opened.append(peer.value)
+            self.local = torch.as_tensor(_DeviceMemory(self._own, self.nbytes), device=self.device)
+        self._flag = torch.zeros(1, dtype=torch.int32, device=self.device)
+        self.fence()
+
+    def view(self, shape, dtype: torch.dtype, offset_bytes: int = 0) -> Tensor:
+        n = 1
+        for s in shape:
+            n *= int(s)
+        nbytes = n * torch.empty((), dtype=dtype).element_size()
+        if offset_bytes % 256 or offset_bytes + nbytes > self.nbytes:
+            raise RuntimeError('torchrua_b200: view does not fit the peer window (offsets are multiples of 256 bytes)')
+        return self.local[offset_bytes:offset_bytes + nbytes].view(dtype).view(tuple(shape))
+
+    def fence(self) -> None:
+        """all ranks' earlier kernels (on their current streams) have finished before anything enqueued
+        after the fence runs.  NCCL: an 4-byte all-reduce, stream-ordered, no host sync.  Other backends
+        (gloo, used by the single-GPU two-process test): device sync + host barrier."""
+        if dist.get_backend(self.group) == 'nccl':
+            dist.all_reduce(self._flag, group=self.group)
+        else:
+            torch.cuda.synchronize(self.device)
+            dist.barrier(group=self.group)
+
+    def close(self) -> None:
+        if getattr(self, '_own', None) is None:
+            return
+        torch.cuda.synchronize(self.device)
+        dist.barrier(group=self.group)      # nobody is still storing into a window that is about to go away
+        self.local = None
+        for p in self._opened:
+            self._lib.rua_peer_window_close(p)
+        self._lib.rua_peer_window_free(self._own)
+        self._own, self._opened, self.ptrs = None, [], []
+
+
+def _pointer_array(values):
+    import ctypes
+    return (ctypes.c_void_p * len(values))(*[v if v else None for v in values])
+
+
+def gather_catted_fused(z, parts: List[Tensor], global_lengths: Tensor, windows: PeerWindows,
+                        offset_bytes: int = 0, local_copy: bool = False):
+    """fused conversion + exchange (2): ``z`` is this rank's shard in ANY layout (C, L, P or R; sequences in
+    the order of ``parts[rank]``).  ONE kernel reads every local token once and stores it at its place in
+    the global C data (original sequence order) inside the window of every rank -- and, with
+    ``local_copy``, also into a contiguous local C buffer (what ``z.cat().data`` would be).
+    Returns the global (N, *) tensor (a view of this rank's window; valid after the trailing fence),
+    or (global, local) with ``local_copy``."""
+    import ctypes
+
+    from torchrua_b200 import _lib, _native
+    from torchrua_b200.core.cast import side_of
+    lib = _lib.load()
+    dev = windows.device
+    rg = z._ragged()
+    src = z.raw()
+    if not src.is_contiguous():
+        src = src.contiguous()
+    feat = tuple(src.shape[1:])
+    row_bytes = src.element_size()
+    for f in feat:
+        row_bytes *= f
+    gl = global_lengths.to(dev, non_blocking=True)
+    goff, gstats = _native.scan(gl)                               # exclusive prefix sum of the GLOBAL lengths
+    base = goff[parts[windows.rank].to(dev, non_blocking=True)]   # first global row of each local sequence
+    n_total = int(global_lengths.sum()) if not global_lengths.is_cuda else int(_native.fetch(gstats)[0])
+    out = windows.view((n_total,) + feat, src.dtype, offset_bytes)
+    dsts = [p + offset_bytes for p in windows.ptrs]
+    bases = [base.data_ptr()] * windows.world
+    local = None
+    if local_copy:
+        local = torch.empty((rg.N,) + feat, dtype=src.dtype, device=dev)
+        dsts.append(local.data_ptr())
+        bases.append(None)
+    side = side_of(z, rg).c_struct()
+    rgc = rg.c_struct()
+    windows.fence()          # peers have finished reading what the previous gather left in their windows
+    with torch.cuda.device(dev):
+        _lib.check(lib.rua_row_map_multi(src.data_ptr(), row_bytes, ctypes.byref(rgc), ctypes.byref(side), rg.N,
+                                         _pointer_array(dsts), _pointer_array(bases), len(dsts), _native._stream()),
+                   'rua_row_map_multi')
+    windows.fence()          # every rank's rows have landed everywhere
+    return (out, local) if local_copy else out
+
+
+def gather_rows_fused(local_rows: Tensor, parts: List[Tensor], windows: PeerWindows, offset_bytes: int = 0,
+                      fence: bool = True) -> Tensor:
+    """exchange (2) for per-sequence outputs (segment reductions, last(), head(1)): row j of ``local_rows``
+    belongs to global sequence ``parts[rank][j]``; one kernel stores it there in every rank's window."""
+    from torchrua_b200 import _lib, _native
+    lib = _lib.load()
+    dev = windows.device
+    rows = local_rows.detach()
+    if not rows.is_contiguous():
+        rows = rows.contiguous()
+    feat = tuple(rows.shape[1:])
+    row_bytes = rows.element_size()
+    for f in feat:
+        row_bytes *= f
+    total = sum(p.numel() for p in parts)
+    out = windows.view((total,) + feat, rows.dtype, offset_bytes)
+    ids = parts[windows.rank].to(dev, non_blocking=True).contiguous()
+    dsts = [p + offset_bytes for p in windows.ptrs]
+    if fence:
+        windows.fence()
+    with torch.cuda.device(dev):
+        _lib.check(lib.rua_scatter_rows_multi(rows.data_ptr(), ids.data_ptr(), rows.shape[0], row_bytes,
+                                              _pointer_array(dsts), len(dsts), _native._stream()),
+                   'rua_scatter_rows_multi')
+    if fence:
+        windows.fence()
+    return out

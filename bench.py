@@ -365,6 +365,12 @@ def run_ours(args):
     h2d = h_data.numel() * 2 + h_lens.numel() * 8
     d2h = h_back.numel() * 2 + h_sum.numel() * 2 * 2
 
+    # ---- output gather (N > 1 only): every rank ends up with the GLOBAL results ----------------------
+    gather = None
+    if world > 1 and not args.no_gather:
+        gather = time_output_gather(args, step, data, lens, lens_host, glens, parts, rank, world, dev, total_tokens,
+                                    barrier)
+
     # ---- CPU baseline (rank 0, single-GPU run only) ------------------------------------------------
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
@@ -391,9 +397,84 @@ def run_ours(args):
                             'streams so that neighbouring steps overlap (PCIe-bound: 2.1 GB each way per step)'},
             'gpu_launches': int(launches), 'clocks': clk,
         }
+        if gather is not None:
+            line['output_gather'] = gather
         emit(line)
     if world > 1:
         dist.destroy_process_group()
+
+
+def time_output_gather(args, step, data, lens, lens_host, glens, parts, rank, world, dev, total_tokens, barrier):
+    """tokens/s WITH the final gather of outputs (every rank receives the global C data in
+    original sequence order plus the global segment_sum / segment_max), two ways:
+      fused   the last conversion of the step (R -> C) stores each row ONCE into the windows of all ranks over
+              NVLink peer mappings (rua_row_map_multi) and into the local C copy the reductions read; the
+              reductions' rows follow through rua_scatter_rows_multi.  Two 4-byte all-reduces as fences.
+      nccl    step(), then all_gather of padded shards + index_put permutation (shard.gather_catted /
+              gather_rows_by_sequence): what one gets from NCCL + torch ops alone.
+    `value` of the bench line stays the no-gather number (the gather is wire-bound: (G-1)/G * N * D bytes per
+    rank over NVLink, not HBM)."""
+    import torch
+    import torch.distributed as dist
+
+    import torchrua_b200 as rua
+    from torchrua_b200 import _native, shard
+    steps = max(3, min(args.steps, 8))
+    b_total = int(glens.numel())
+    row = HIDDEN * 2
+    sum_off = (total_tokens * row + 255) // 256 * 256
+    max_off = sum_off + (b_total * row + 255) // 256 * 256
+    windows = shard.PeerWindows(max_off + b_total * row)
+    glens_dev = glens.to(dev)
+
+    def fused_step():
+        _native._CACHE.clear()
+        right = rua.C(data=data, token_sizes=lens).pack().left(0).right(0)
+        windows.fence()
+        full, back = shard.gather_catted_fused(right, parts, glens_dev, windows, local_copy=True, fence=False)
+        s = rua.segment_sum(back, lens)
+        m = rua.segment_max(back, lens)
+        gs = shard.gather_rows_fused(s, parts, windows, offset_bytes=sum_off, fence=False)
+        gm = shard.gather_rows_fused(m, parts, windows, offset_bytes=max_off, fence=False)
+        windows.fence()
+        return full, gs, gm
+
+    def nccl_step():
+        back, s, m = step(data, lens)
+        full = shard.gather_catted(back.data, lens, parts, glens_dev)
+        gs = shard.gather_rows_by_sequence(s, parts)
+        gm = shard.gather_rows_by_sequence(m, parts)
+        return full, gs, gm
+
+    def timed(fn):
+        for _ in range(2):
+            out = fn()
+        barrier()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(steps):
+            out = fn()
+        b.record()
+        barrier()
+        ms = torch.tensor([a.elapsed_time(b)], dtype=torch.double, device=dev)
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return out, float(ms) / steps
+
+    (f_full, f_s, f_m), f_ms = timed(fused_step)
+    (n_full, n_s, n_m), n_ms = timed(nccl_step)
+    same = bool(torch.equal(f_full, n_full) and torch.equal(f_s, n_s) and torch.equal(f_m, n_m))
+    # the global C data restricted to this rank's sequences is this rank's input (round trip = identity)
+    del n_full, n_s, n_m
+    wire = (world - 1) * int(lens_host.sum()) * row
+    res = {'what': 'the same step, but every rank ends with the global C data + global segment_sum / segment_max',
+           'fused_peer_store': {'ms_per_step': f_ms, 'value': total_tokens / (f_ms * 1e-3), 'unit': 'tokens/s',
+                                'nvlink_out_GBs_per_rank': wire / (f_ms * 1e-3) / 1e9},
+           'nccl_all_gather_then_permute': {'ms_per_step': n_ms, 'value': total_tokens / (n_ms * 1e-3),
+                                            'unit': 'tokens/s'},
+           'results_identical': same, 'steps': steps,
+           'wire_bytes_out_per_rank_per_step': wire}
+    windows.close()
+    return res
 
 
 _JSON_FD = None
@@ -425,6 +506,7 @@ def main():
     ap.add_argument('--warmup', type=int, default=5)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--no-cpu', action='store_true', help='skip the cpu_baseline leg')
+    ap.add_argument('--no-gather', action='store_true', help='skip the output-gather legs of multi-GPU runs')
     args = ap.parse_args()
     if args.impl == 'reference':
         run_reference(args)

@@ -208,13 +208,15 @@ def _pointer_array(values):
 
 
 def gather_catted_fused(z, parts: List[Tensor], global_lengths: Tensor, windows: PeerWindows,
-                        offset_bytes: int = 0, local_copy: bool = False):
+                        offset_bytes: int = 0, local_copy: bool = False, fence: bool = True):
     """fused conversion + exchange (2): ``z`` is this rank's shard in ANY layout (C, L, P or R; sequences in
     the order of ``parts[rank]``).  ONE kernel reads every local token once and stores it at its place in
     the global C data (original sequence order) inside the window of every rank -- and, with
     ``local_copy``, also into a contiguous local C buffer (what ``z.cat().data`` would be).
     Returns the global (N, *) tensor (a view of this rank's window; valid after the trailing fence),
-    or (global, local) with ``local_copy``."""
+    or (global, local) with ``local_copy``.  ``fence=False`` leaves both fences to the caller (several
+    gathers into disjoint parts of the window can share one pair: ``windows.fence()`` before the first store
+    and after the last)."""
     import ctypes
 
     from torchrua_b200 import _lib, _native
@@ -243,12 +245,14 @@ def gather_catted_fused(z, parts: List[Tensor], global_lengths: Tensor, windows:
         bases.append(None)
     side = side_of(z, rg).c_struct()
     rgc = rg.c_struct()
-    windows.fence()          # peers have finished reading what the previous gather left in their windows
+    if fence:
+        windows.fence()      # peers have finished reading what the previous gather left in their windows
     with torch.cuda.device(dev):
         _lib.check(lib.rua_row_map_multi(src.data_ptr(), row_bytes, ctypes.byref(rgc), ctypes.byref(side), rg.N,
                                          _pointer_array(dsts), _pointer_array(bases), len(dsts), _native._stream()),
                    'rua_row_map_multi')
-    windows.fence()          # every rank's rows have landed everywhere
+    if fence:
+        windows.fence()      # every rank's rows have landed everywhere
     return (out, local) if local_copy else out
 
 

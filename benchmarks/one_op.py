@@ -40,6 +40,14 @@ if name.startswith('cfg5'):
     elif name == 'cfg5_bmask':
         c = rua.C(data=torch.arange(n, device='cuda'), token_sizes=lens)
         fn = lambda: c.bmask()
+    elif name == 'cfg5_all':       # every index-only / narrow-row op of config 5 once (one ncu pass over all kernels)
+        c = rua.C(data=torch.arange(n, device='cuda'), token_sizes=lens)
+        left, pk = c.left(0), c.pack()
+        x = torch.randn(n, device='cuda')
+
+        def fn():
+            return (c.bmask(), c.mask(0, 1, torch.long), c.ptr(), pk.ptr(), left.idx(), c.pack(), c.left(0), pk.cat(),
+                    left.cat(), c.rev(), rua.segment_sum(x, lens), rua.segment_max(x, lens))
     else:
         raise SystemExit(f'unknown op {name}')
 elif name.startswith('cfg3'):

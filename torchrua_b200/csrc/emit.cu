@@ -8,17 +8,30 @@
 // arange, new_full and index_put_.  Here every output element is a closed form of (segment, within)
 // and is stored once with 16-byte coalesced stores.  HBM-write bound.
 #include "common.cuh"
+#include "tile_decode.cuh"
 
 namespace rua {
 
 // ------------------------------------------------------------------------------------------------
 // mask: out[i, t] = t < len[i] ? one : zero          (left aligned for all layouts, mask.py:10)
-// each thread produces 16 bytes = 16/E consecutive elements of the flattened (B, W) output
+// Each thread produces 32 bytes = 32/E consecutive elements of the flattened (B, W) output and stores them
+// with one 256-bit store.  When the span lies inside one row (the common case: W is a multiple of the span or
+// simply long) the 32 bytes are built word-wise from the count of leading `one`s -- a handful of instructions
+// per 8 bytes instead of a compare / select / row-wrap check per element (bool masks: 32 elements per thread).
 // ------------------------------------------------------------------------------------------------
+template <typename E> __device__ __forceinline__ unsigned long long replicate64(E v) {
+  unsigned long long x = (unsigned long long)v;
+  if (sizeof(E) < 2) x |= x << 8;
+  if (sizeof(E) < 4) x |= x << 16;
+  if (sizeof(E) < 8) x |= x << 32;
+  return x;
+}
+
 template <typename E>
 __global__ void __launch_bounds__(256)
-mask_kernel(const int64_t* __restrict__ len, int64_t B, int64_t W, E zero, E one, E* __restrict__ out) {
-  constexpr int K = 16 / sizeof(E);
+mask_kernel(const int64_t* __restrict__ len, int64_t B, int64_t W, E zero, E one, E* __restrict__ out, int wide) {
+  constexpr int K = 32 / sizeof(E);      // elements per thread
+  constexpr int EPW = 8 / sizeof(E);     // elements per 64-bit word
   const int64_t total = B * W;
   const int64_t g0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * K;
   if (g0 >= total) return;
@@ -32,96 +45,92 @@ mask_kernel(const int64_t* __restrict__ len, int64_t B, int64_t W, E zero, E one
     t = g0 - i * W;
   }
   int64_t li = __ldg(len + i);
-  union { uint4 v; E e[K]; } u;
+  union { unsigned long long w[4]; uint4 v[2]; E e[K]; } u;
+  if (t + K <= W) {
+    const int64_t rest = li - t;
+    const int ones = rest <= 0 ? 0 : (rest >= K ? K : (int)rest);   // leading `one`s of this span
+    const unsigned long long ow = replicate64<E>(one), zw = replicate64<E>(zero);
 #pragma unroll
-  for (int k = 0; k < K; ++k) {
-    u.e[k] = t < li ? one : zero;
-    if (++t == W) {
-      t = 0;
-      ++i;
-      li = i < B ? __ldg(len + i) : 0;
+    for (int w = 0; w < 4; ++w) {
+      const int n1 = ones - w * EPW;
+      const unsigned long long m = n1 >= EPW ? ~0ull : (n1 <= 0 ? 0ull : ((1ull << (n1 * 8 * (int)sizeof(E) & 63)) - 1ull));
+      u.w[w] = (ow & m) | (zw & ~m);
+    }
+  } else {
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+      u.e[k] = t < li ? one : zero;
+      if (++t == W) {
+        t = 0;
+        ++i;
+        li = i < B ? __ldg(len + i) : 0;
+      }
     }
   }
   if (g0 + K <= total) {
-    __stcs(reinterpret_cast<uint4*>(out + g0), u.v);
+    if (wide) {
+      asm volatile("st.global.cs.v4.b64 [%0], {%1, %2, %3, %4};" ::"l"(out + g0), "l"(u.w[0]), "l"(u.w[1]), "l"(u.w[2]), "l"(u.w[3]) : "memory");
+    } else {
+      __stcs(reinterpret_cast<uint4*>(out + g0), u.v[0]);
+      __stcs(reinterpret_cast<uint4*>(out + g0) + 1, u.v[1]);
+    }
   } else {
     for (int k = 0; g0 + k < total; ++k) out[g0 + k] = u.e[k];
   }
 }
 
 // ------------------------------------------------------------------------------------------------
-// ptr / idx emit over a segmented range.  A CTA owns a tile of kEmitTile consecutive positions.
-// The segment boundaries that fall inside the tile are staged in shared memory (one cooperative
-// 32-ary search finds the first one), so each element resolves its segment with a short
-// shared-memory binary search instead of a log2(S)-deep walk over global memory.
+// ptr / idx emit over a segmented range.  A CTA owns a tile of kDecTile consecutive positions and decodes
+// it once (tile_decode.cuh: staged segment starts + a block scan of start counters), after which every
+// position resolves its segment with two shared-memory reads.  A thread emits 4 consecutive positions =
+// one 256-bit store per output (sm_100: STG.E.ENL2.256, a full 32-byte sector per lane).
 // ------------------------------------------------------------------------------------------------
-constexpr int kEmitThreads = 256;
-constexpr int kEmitGroup = 4;                                   // consecutive positions per thread = one 256-bit store
-constexpr int kEmitRounds = 2;
-constexpr int kEmitTile = kEmitThreads * kEmitGroup * kEmitRounds;  // 2048 positions per CTA
-constexpr int kEmitCap = kEmitTile + 2;                            // segment starts staged per tile
+constexpr int kEmitThreads = kDecThreads;
+constexpr int kEmitGroup = 4;
+constexpr int kEmitRounds = kDecTile / (kEmitThreads * kEmitGroup);  // 2
+constexpr int kEmitTile = kDecTile;
 
-// sm_100a has 256-bit global stores (SASS STG.E.ENL2.256): one full 32-byte sector per lane
 __device__ __forceinline__ void st_v4_i64(int64_t* p, const int64_t* v) {
-  asm volatile("st.global.v4.b64 [%0], {%1, %2, %3, %4};" ::"l"(p), "l"(v[0]), "l"(v[1]), "l"(v[2]), "l"(v[3]) : "memory");
+  asm volatile("st.global.cs.v4.b64 [%0], {%1, %2, %3, %4};" ::"l"(p), "l"(v[0]), "l"(v[1]), "l"(v[2]), "l"(v[3]) : "memory");
 }
 
 __global__ void __launch_bounds__(kEmitThreads)
 emit_ptr_kernel(const int64_t* __restrict__ off, int64_t S, int64_t n, const int64_t* __restrict__ relabel,
                 int64_t* __restrict__ which, int64_t* __restrict__ within, int64_t* __restrict__ flat,
                 int64_t stride, int right_align, int wide_stores) {
-  __shared__ int s_rel[kEmitCap];          // tile-relative segment starts, clamped to [-1, tile + 1]
-  __shared__ int64_t s_first, s_last;
+  __shared__ TileDecodeSmem sm;
   const int tid = threadIdx.x;
   const int64_t j0 = (int64_t)blockIdx.x * kEmitTile;
   const int nj = (int)(j0 + kEmitTile < n ? kEmitTile : n - j0);
   GlobalOff g{off};
-  // two warp-cooperative 32-ary searches (log32 S dependent round trips instead of log2 S)
-  if (tid < 32) {
-    const int64_t a = warp_owner_search(g, S, j0, tid);
-    if (tid == 0) s_first = a;
-  } else if (tid < 64) {
-    const int64_t b = warp_owner_search(g, S, j0 + nj - 1, tid - 32);
-    if (tid == 32) s_last = b;
-  }
-  __syncthreads();
-  const int64_t first = s_first, last = s_last;
-  const int64_t cnt64 = last - first + 2;  // off[first .. last+1]
-  const bool staged = cnt64 <= kEmitCap;   // many empty segments inside the tile can overflow the stage
-  const int cnt = staged ? (int)cnt64 : 0;
-  if (staged) {
-    for (int k = tid; k < cnt; k += kEmitThreads) {
-      const int64_t d = __ldg(off + first + k) - j0;
-      s_rel[k] = d < -1 ? -1 : (d > kEmitTile + 1 ? kEmitTile + 1 : (int)d);
-    }
-  }
-  __syncthreads();
-  const int64_t off_first = __ldg(off + first);  // the only staged start that can lie before the tile
+  const TileDecode d = tile_decode(g, S, j0, nj, sm);
 
 #pragma unroll
   for (int r = 0; r < kEmitRounds; ++r) {
     const int jb = (r * kEmitThreads + tid) * kEmitGroup;  // tile-relative, 4 consecutive positions
     if (jb >= nj) break;
     int64_t sv[kEmitGroup], wv[kEmitGroup], fv[kEmitGroup];
-    if (staged) {
-      int lo = 0, hi = cnt - 1;              // one search for the group's first position ...
-      while (hi - lo > 1) {
-        const int mid = (lo + hi) >> 1;
-        if (s_rel[mid] <= jb) lo = mid; else hi = mid;
-      }
+    if (d.staged) {
+      const int4 k4 = reinterpret_cast<const int4*>(sm.seg)[jb >> 2];
+      const int kk[kEmitGroup] = {k4.x, k4.y, k4.z, k4.w};
+      int k_prev = -1, rel = 0;
+      int64_t shift = 0;   // flat = which * stride + within + shift
 #pragma unroll
-      for (int k = 0; k < kEmitGroup; ++k) {  // ... then walk: a group rarely crosses more than one boundary
-        const int jr = jb + k;
-        while (lo + 2 < cnt && s_rel[lo + 1] <= jr) ++lo;
-        const int64_t base = lo == 0 ? off_first : j0 + s_rel[lo];
-        const int64_t j = j0 + jr;
-        sv[k] = first + lo;
-        wv[k] = j - base;
-        if (flat) {
-          const int64_t len = (s_rel[lo + 1] <= kEmitTile && lo > 0) ? (int64_t)(s_rel[lo + 1] - s_rel[lo])
-                                                                      : __ldg(off + first + lo + 1) - base;
-          fv[k] = sv[k] * stride + wv[k] + (right_align ? stride - len : 0);
+      for (int e = 0; e < kEmitGroup; ++e) {
+        const int k = kk[e];
+        if (k != k_prev) {                  // a group rarely crosses a boundary: one lookup for all four
+          k_prev = k;
+          rel = sm.rel[k];
+          if (flat) {
+            const int nxt = sm.rel[k + 1];
+            const int64_t len = (k > 0 && nxt <= kEmitTile) ? (int64_t)(nxt - rel)
+                                                            : __ldg(off + d.first + k + 1) - __ldg(off + d.first + k);
+            shift = right_align ? stride - len : 0;
+          }
         }
+        sv[e] = d.first + k;
+        wv[e] = k == 0 ? (j0 + jb + e) - d.off_first : (int64_t)(jb + e - rel);
+        fv[e] = sv[e] * stride + wv[e] + shift;
       }
     } else {
 #pragma unroll
@@ -169,14 +178,15 @@ int rua_mask(const int64_t* len, int64_t B, int64_t W, const void* zero_host, co
   if (((uintptr_t)out & 15u) != 0) return RUA_ERR_INVALID;
   cudaStream_t st = (cudaStream_t)stream;
   const int64_t total = B * W;
-  const int64_t per = 16 / elem_bytes;
+  const int64_t per = 32 / elem_bytes;
   const int64_t blocks = ceil_div(ceil_div(total, per), 256);
+  const int wide = ((uintptr_t)out & 31u) == 0;
   if (blocks >= (1ll << 31)) return RUA_ERR_UNSUPPORTED;
   switch (elem_bytes) {
-    case 1: mask_kernel<uint8_t><<<(unsigned)blocks, 256, 0, st>>>(len, B, W, *(const uint8_t*)zero_host, *(const uint8_t*)one_host, (uint8_t*)out); break;
-    case 2: mask_kernel<uint16_t><<<(unsigned)blocks, 256, 0, st>>>(len, B, W, *(const uint16_t*)zero_host, *(const uint16_t*)one_host, (uint16_t*)out); break;
-    case 4: mask_kernel<uint32_t><<<(unsigned)blocks, 256, 0, st>>>(len, B, W, *(const uint32_t*)zero_host, *(const uint32_t*)one_host, (uint32_t*)out); break;
-    case 8: mask_kernel<uint64_t><<<(unsigned)blocks, 256, 0, st>>>(len, B, W, *(const uint64_t*)zero_host, *(const uint64_t*)one_host, (uint64_t*)out); break;
+    case 1: mask_kernel<uint8_t><<<(unsigned)blocks, 256, 0, st>>>(len, B, W, *(const uint8_t*)zero_host, *(const uint8_t*)one_host, (uint8_t*)out, wide); break;
+    case 2: mask_kernel<uint16_t><<<(unsigned)blocks, 256, 0, st>>>(len, B, W, *(const uint16_t*)zero_host, *(const uint16_t*)one_host, (uint16_t*)out, wide); break;
+    case 4: mask_kernel<uint32_t><<<(unsigned)blocks, 256, 0, st>>>(len, B, W, *(const uint32_t*)zero_host, *(const uint32_t*)one_host, (uint32_t*)out, wide); break;
+    case 8: mask_kernel<uint64_t><<<(unsigned)blocks, 256, 0, st>>>(len, B, W, *(const uint64_t*)zero_host, *(const uint64_t*)one_host, (uint64_t*)out, wide); break;
     default: return RUA_ERR_INVALID;
   }
   return check_launch();

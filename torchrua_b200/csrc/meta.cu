@@ -179,39 +179,62 @@ radix_hist_kernel(SortSrc src, int64_t n, int shift, uint32_t* __restrict__ tabl
   table[(size_t)threadIdx.x * nblk + blockIdx.x] = hist[threadIdx.x];
 }
 
-// exclusive scan of `count` uint32 entries by one CTA of 1024 threads
-__global__ void __launch_bounds__(1024) table_scan_kernel(uint32_t* table, int64_t count) {
-  __shared__ uint32_t s_part[1024];
-  const int tid = threadIdx.x;
-  int64_t per = ceil_div(count, 1024);
-  int64_t lo = tid * per, hi = lo + per < count ? lo + per : count;
-  uint32_t sum = 0;
-  for (int64_t i = lo; i < hi; ++i) sum += table[i];
-  s_part[tid] = sum;
-  __syncthreads();
-  // Hillis-Steele over 1024 partials
-  for (int d = 1; d < 1024; d <<= 1) {
-    uint32_t o = tid >= d ? s_part[tid - d] : 0;
+// The digit table is digit-major: table[d * nblk + b] = count of digit d in block b.  Its exclusive scan
+// is done in two levels so that no single CTA walks all 256 * nblk entries (a 1M-element sort has 125 K of
+// them: 106 us on one CTA): here one CTA per digit scans its own row in place and records the row total;
+// the scatter kernel turns the 256 totals into digit bases with a block scan of its own.
+__global__ void __launch_bounds__(256) table_row_scan_kernel(uint32_t* table, int nblk, uint32_t* __restrict__ totals) {
+  __shared__ uint32_t s_warp[8];
+  uint32_t* row = table + (size_t)blockIdx.x * nblk;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  uint32_t carry = 0;
+  for (int base = 0; base < nblk; base += 256) {
+    const int i = base + tid;
+    const uint32_t x = i < nblk ? row[i] : 0;
+    uint32_t incl = x;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const uint32_t o = __shfl_up_sync(kFullMask, incl, d);
+      if (lane >= d) incl += o;
+    }
+    if (lane == 31) s_warp[warp] = incl;
     __syncthreads();
-    s_part[tid] += o;
+    uint32_t wbase = 0, total = 0;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) {
+      const uint32_t t = s_warp[w];
+      if (w < warp) wbase += t;
+      total += t;
+    }
+    if (i < nblk) row[i] = carry + wbase + incl - x;
+    carry += total;
     __syncthreads();
   }
-  uint32_t run = s_part[tid] - sum;
-  for (int64_t i = lo; i < hi; ++i) {
-    uint32_t x = table[i];
-    table[i] = run;
-    run += x;
-  }
+  if (tid == 0) totals[blockIdx.x] = carry;
 }
 
 __global__ void __launch_bounds__(kSortThreads)
-radix_scatter_kernel(SortSrc src, int64_t n, int shift, const uint32_t* __restrict__ table, int nblk,
-                     uint32_t* __restrict__ keys_out, uint32_t* __restrict__ vals_out,
+radix_scatter_kernel(SortSrc src, int64_t n, int shift, const uint32_t* __restrict__ table,
+                     const uint32_t* __restrict__ totals, int nblk, uint32_t* __restrict__ keys_out, uint32_t* __restrict__ vals_out,
                      int64_t* __restrict__ sorted, int64_t* __restrict__ unsorted) {
   __shared__ uint32_t whist[kSortWarps][kRadix];
+  __shared__ uint32_t s_dwarp[kSortWarps];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   for (int i = tid; i < kSortWarps * kRadix; i += kSortThreads) (&whist[0][0])[i] = 0;
+  // digit base = exclusive scan of the 256 row totals (one digit per thread)
+  const uint32_t dtotal = totals[tid];
+  uint32_t dincl = dtotal;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    const uint32_t o = __shfl_up_sync(kFullMask, dincl, d);
+    if (lane >= d) dincl += o;
+  }
+  if (lane == 31) s_dwarp[warp] = dincl;
   __syncthreads();
+  uint32_t dbase = dincl - dtotal;
+#pragma unroll
+  for (int w = 0; w < kSortWarps; ++w)
+    if (w < warp) dbase += s_dwarp[w];
 
   // warp w owns the contiguous range [base + w*256, base + (w+1)*256), visited in 8 rounds of 32
   const int64_t wbase = (int64_t)blockIdx.x * kSortTile + (int64_t)warp * (32 * kSortRounds);
@@ -235,7 +258,7 @@ radix_scatter_kernel(SortSrc src, int64_t n, int shift, const uint32_t* __restri
   }
   __syncthreads();
   {  // one thread per digit: turn per-warp counts into global start positions
-    uint32_t run = table[(size_t)tid * nblk + blockIdx.x];
+    uint32_t run = dbase + table[(size_t)tid * nblk + blockIdx.x];
 #pragma unroll
     for (int w = 0; w < kSortWarps; ++w) {
       uint32_t c = whist[w][tid];
@@ -269,17 +292,29 @@ __global__ void invert_perm_kernel(const int64_t* __restrict__ perm, int64_t n, 
   if (j < n) out[perm[j]] = j;
 }
 
-// bs[t] = first r with len[sorted[r]] <= t  (len o sorted is non-increasing)
-__global__ void batch_sizes_kernel(const int64_t* __restrict__ len, const int64_t* __restrict__ sorted,
-                                   int64_t B, int64_t T, int64_t* __restrict__ bs) {
-  int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+// bs[t] = first r with len[sorted[r]] <= t  (len o sorted is non-increasing).  One WARP per time step:
+// a 32-ary search needs log32(B) rounds of two dependent loads instead of log2(B) (B = 1M: 4 rounds, not 20;
+// this kernel is pure latency -- T searches over an L2-resident array).
+__global__ void __launch_bounds__(256)
+batch_sizes_kernel(const int64_t* __restrict__ len, const int64_t* __restrict__ sorted, int64_t B, int64_t T,
+                   int64_t* __restrict__ bs) {
+  const int lane = threadIdx.x & 31;
+  const int64_t t = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (t >= T) return;
   int64_t lo = 0, hi = B;  // invariant: all r < lo have len > t; all r >= hi have len <= t
   while (lo < hi) {
-    int64_t mid = (lo + hi) >> 1;
-    if (__ldg(len + __ldg(sorted + mid)) > t) lo = mid + 1; else hi = mid;
+    const int64_t n = hi - lo;
+    const int64_t step = (n + 31) / 32;
+    const int64_t probe = lo + (int64_t)lane * step;       // probes lo, lo+step, ... (monotone predicate)
+    const bool gt = probe < hi && __ldg(len + __ldg(sorted + probe)) > t;
+    const int k = __popc(__ballot_sync(kFullMask, gt));    // k leading probes still have len > t
+    if (k == 0) { hi = lo; break; }
+    const int64_t last_gt = lo + (int64_t)(k - 1) * step;   // len > t here
+    const int64_t nxt = last_gt + step;                     // first probe with len <= t (or beyond hi)
+    lo = last_gt + 1;
+    hi = nxt < hi ? nxt : hi;
   }
-  bs[t] = lo;
+  if (lane == 0) bs[t] = lo;
 }
 
 // len[i] = first t with bs[t] <= unsorted[i]  (bs is non-increasing)
@@ -367,8 +402,8 @@ int rua_scan_lengths(const int64_t* sizes, int64_t n, int64_t clamp_max, int64_t
 size_t rua_sort_workspace_bytes(int64_t B) {
   if (B <= 0) return 16;
   int64_t nblk = ceil_div(B, kSortTile);
-  // 2 x (keys, vals) ping-pong + digit table
-  return (size_t)(4 * B + (int64_t)kRadix * nblk) * sizeof(uint32_t) + 64;
+  // 2 x (keys, vals) ping-pong + digit table + digit totals
+  return (size_t)(4 * B + (int64_t)kRadix * nblk + kRadix) * sizeof(uint32_t) + 64;
 }
 
 static int sort_impl(const int64_t* len, int64_t B, int64_t T, int ascending, int64_t* sorted, int64_t* unsorted,
@@ -397,6 +432,7 @@ static int sort_impl(const int64_t* len, int64_t B, int64_t T, int ascending, in
   uint32_t* keys[2] = {w, w + B};
   uint32_t* vals[2] = {w + 2 * B, w + 3 * B};
   uint32_t* table = w + 4 * B;
+  uint32_t* totals = table + (size_t)kRadix * nblk;
 
   int bits = 0;
   while (bits < 32 && (T >> bits) != 0) ++bits;
@@ -412,10 +448,10 @@ static int sort_impl(const int64_t* len, int64_t B, int64_t T, int ascending, in
     radix_hist_kernel<<<nblk, kSortThreads, 0, st>>>(src, B, shift, table, nblk);
     int rc = check_launch();
     if (rc) return rc;
-    table_scan_kernel<<<1, 1024, 0, st>>>(table, (int64_t)kRadix * nblk);
+    table_row_scan_kernel<<<kRadix, 256, 0, st>>>(table, nblk, totals);
     rc = check_launch();
     if (rc) return rc;
-    radix_scatter_kernel<<<nblk, kSortThreads, 0, st>>>(src, B, shift, table, nblk, keys[p & 1], vals[p & 1],
+    radix_scatter_kernel<<<nblk, kSortThreads, 0, st>>>(src, B, shift, table, totals, nblk, keys[p & 1], vals[p & 1],
                                                         last ? sorted : nullptr, last ? unsorted : nullptr);
     rc = check_launch();
     if (rc) return rc;
@@ -436,7 +472,7 @@ int rua_batch_sizes(const int64_t* len, const int64_t* sorted, int64_t B, int64_
   if (B < 0 || T < 0) return RUA_ERR_INVALID;
   if (T == 0) return RUA_OK;
   if (!len || !sorted || !bs) return RUA_ERR_INVALID;
-  batch_sizes_kernel<<<(unsigned)ceil_div(T, 256), 256, 0, (cudaStream_t)stream>>>(len, sorted, B, T, bs);
+  batch_sizes_kernel<<<(unsigned)ceil_div(T, 8), 256, 0, (cudaStream_t)stream>>>(len, sorted, B, T, bs);
   return check_launch();
 }
 

@@ -17,6 +17,7 @@
 #include <cstdlib>
 
 #include "common.cuh"
+#include "tile_decode.cuh"
 
 namespace rua {
 
@@ -36,7 +37,39 @@ struct RowMapParams {
   int32_t col_splits;      // gridDim.y
   const int64_t* gather_index;   // explicit source rows (rua_gather_rows) or NULL
   const int64_t* scatter_index;  // explicit destination rows (rua_scatter_rows) or NULL
+  uint32_t div_wrv_m, div_wrv_s;  // narrow padded destinations: x / (width * row_vecs) for x < 2^31 (FastDiv)
+  uint32_t div_rv_m, div_rv_s;    //                             x / row_vecs
 };
+
+// unsigned division of x < 2^31 by a divisor fixed at launch: q = (x * m) >> s with m = floor(2^s / d) + 1,
+// s = 31 + ceil(log2 d) (Granlund-Montgomery, N = 31); two instructions instead of the ~20 of a runtime
+// 32-bit division -- the narrow-row kernels are issue-bound and divide once per 8-byte element
+struct FastDiv {
+  uint32_t m, s;
+  __host__ static FastDiv make(uint64_t d) {
+    FastDiv f;
+    uint32_t l = 0;
+    while ((1ull << l) < d) ++l;
+    f.s = 31 + l;
+    f.m = (uint32_t)((1ull << f.s) / d + 1);
+    return f;
+  }
+};
+__device__ __forceinline__ uint32_t fast_div(uint32_t x, uint32_t m, uint32_t s) {
+  return (uint32_t)(((unsigned long long)x * m) >> s);
+}
+
+constexpr int kGenericSrc = -1;   // template tag: full generality (selects, transformed lengths, pad quirks)
+
+// "simple" maps = the 12 layout conversions: identity token map, untransformed lengths, plain fill.  With the
+// source layout known at compile time the per-element address is 2-4 instructions and no branches.
+template <int SRC>
+__device__ __forceinline__ int64_t simple_source_row(const RowMapParams& p, int64_t i, int64_t td, int64_t len) {
+  if (SRC == RUA_CAT) return __ldg(p.rg.off + i) + td;
+  if (SRC == RUA_LEFT) return i * p.s.width + td;
+  if (SRC == RUA_RIGHT) return i * p.s.width + (p.s.width - len) + td;
+  return __ldg(p.rg.poff + td) + __ldg(p.rg.unsorted + i);
+}
 
 constexpr int64_t kPadRow = -1;
 constexpr int64_t kNoRow = -2;
@@ -352,14 +385,15 @@ constexpr int kTileThreads = 256;
 constexpr int kTileItems = 8;
 constexpr int kTileVecs = kTileThreads * kTileItems;  // 2048 destination vectors per CTA
 constexpr int kTileCap = kTileVecs + 2;               // staged segment starts
+static_assert(kTileThreads == kDecThreads && kTileVecs == kDecTile, "tile_decode.cuh assumes the same tile shape");
 
-template <typename V, typename OffFn>
-__device__ __forceinline__ void tile_body(const RowMapParams& p, OffFn f, int64_t S, int* s_rel,
-                                          int64_t* s_bounds) {
+template <typename V, int SRC, typename OffFn>
+__device__ __forceinline__ void tile_body(const RowMapParams& p, OffFn f, int64_t S, TileDecodeSmem& sm) {
   // Everything inside a tile is 32-bit and tile-relative (a tile spans 2048 vectors): these kernels are
-  // ISSUE-bound (ncu: 65 % issue-active at 19 % DRAM), so 64-bit divisions and 64-bit shared-memory
-  // searches are what they cannot afford.
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  // ISSUE-bound (ncu: 65 % issue-active at 19 % DRAM), so 64-bit divisions and per-row searches are what
+  // they cannot afford.  The tile's destination rows are decoded once (tile_decode.cuh); a row then finds
+  // its segment with two shared-memory reads.
+  const int tid = threadIdx.x;
   const int64_t total = p.d.rows * p.row_vecs;
   const int64_t e0 = (int64_t)blockIdx.x * kTileVecs;
   const int n_e = (int)(e0 + kTileVecs < total ? kTileVecs : total - e0);  // vectors in this tile
@@ -367,25 +401,10 @@ __device__ __forceinline__ void tile_body(const RowMapParams& p, OffFn f, int64_
   const int64_t r0 = rv == 1 ? e0 : e0 / rv;                                // first destination row
   const uint32_t c0 = rv == 1 ? 0u : (uint32_t)(e0 - r0 * rv);              // column of the first vector
   const int64_t r1 = rv == 1 ? e0 + n_e - 1 : (e0 + n_e - 1) / rv;          // last destination row
-  if (warp == 0) {
-    int64_t a = warp_owner_search(f, S, r0, lane);
-    if (lane == 0) s_bounds[0] = a;
-  } else if (warp == 1) {
-    int64_t b = warp_owner_search(f, S, r1, lane);
-    if (lane == 0) s_bounds[1] = b;
-  }
-  __syncthreads();
-  const int64_t first = s_bounds[0], last = s_bounds[1];
-  const int64_t cnt64 = last - first + 2;        // f(first) .. f(last + 1)
-  const bool staged = cnt64 <= kTileCap;         // runs of empty segments can overflow the stage
-  const int cnt = staged ? (int)cnt64 : 0;
-  if (staged) {
-    for (int k = tid; k < cnt; k += kTileThreads) {
-      int64_t d = f(first + k) - r0;             // tile-relative start of segment first+k
-      s_rel[k] = d < -1 ? -1 : (d > kTileVecs + 1 ? kTileVecs + 1 : (int)d);
-    }
-  }
-  __syncthreads();
+  const TileDecode dec = tile_decode(f, S, r0, (int)(r1 - r0 + 1), sm);
+  const bool staged = dec.staged;
+  const int64_t first = dec.first;
+  const int* s_rel = sm.rel;
 
   const V* __restrict__ src = reinterpret_cast<const V*>(p.src);
   V* __restrict__ dst = reinterpret_cast<V*>(p.dst) + e0;
@@ -405,15 +424,9 @@ __device__ __forceinline__ void tile_body(const RowMapParams& p, OffFn f, int64_
       int64_t s, base;
       int64_t base_len = -1;
       if (staged) {
-        int lo = 0, hi = cnt - 1;
-        while (hi - lo > 1) {
-          const int mid = (lo + hi) >> 1;
-          if (s_rel[mid] <= (int)jr) lo = mid; else hi = mid;
-        }
+        const int lo = sm.seg[jr];               // segments first+1 .. first+lo start at or before this row
         s = first + lo;
-        base = r0 + s_rel[lo];                   // exact: s_rel[lo] <= jr means it was not clamped high,
-                                                 // and only segment `first` can start before the tile
-        if (lo == 0) base = f(first);
+        base = lo == 0 ? dec.off_first : r0 + s_rel[lo];
         if (len_from_stage && lo > 0 && s_rel[lo + 1] <= kTileVecs) base_len = s_rel[lo + 1] - s_rel[lo];
       } else {
         s = owner_search(f, S, r0 + jr);
@@ -423,9 +436,15 @@ __device__ __forceinline__ void tile_body(const RowMapParams& p, OffFn f, int64_
       int64_t i, td;
       if (is_pack) { td = s; i = __ldg(p.rg.sorted + (j - base)); }
       else { i = s; td = j - base; }
-      if (base_len < 0) base_len = __ldg(p.rg.off + i + 1) - __ldg(p.rg.off + i);
-      int64_t sr = source_row(p, i, td, base_len);
-      if (sr == kPadRow && p.pad_mode == RUA_PAD_ROW0) sr = 0;
+      int64_t sr;
+      if (SRC == kGenericSrc) {
+        if (base_len < 0) base_len = __ldg(p.rg.off + i + 1) - __ldg(p.rg.off + i);
+        sr = source_row(p, i, td, base_len);
+        if (sr == kPadRow && p.pad_mode == RUA_PAD_ROW0) sr = 0;
+      } else {                                   // conversions: every destination token of C / P exists in the source
+        if (SRC == RUA_RIGHT && base_len < 0) base_len = __ldg(p.rg.off + i + 1) - __ldg(p.rg.off + i);
+        sr = simple_source_row<SRC>(p, i, td, base_len);
+      }
       srow[r] = sr;
     }
   }
@@ -442,19 +461,18 @@ __device__ __forceinline__ void tile_body(const RowMapParams& p, OffFn f, int64_
 }
 
 // destination C or P: segment search through shared memory
-template <typename V>
+template <typename V, int SRC>
 __global__ void __launch_bounds__(kTileThreads)
 row_map_tile_kernel(const RowMapParams p) {
-  __shared__ int s_rel[kTileCap];
-  __shared__ int64_t s_bounds[2];
+  __shared__ TileDecodeSmem sm;
   if (p.d.layout == RUA_CAT) {
     CatOff f{p.rg.off, p.d.len_xform, p.d.len_arg};
-    tile_body<V>(p, f, p.rg.B, s_rel, s_bounds);
+    tile_body<V, SRC>(p, f, p.rg.B, sm);
   } else {
     const int64_t sh = pack_shift(p.d);
     PackOff f{p.rg.poff, sh};
     const int64_t steps = p.d.len_xform == RUA_LEN_CONST ? p.d.len_arg : p.rg.Tp - sh;
-    tile_body<V>(p, f, steps, s_rel, s_bounds);
+    tile_body<V, SRC>(p, f, steps, sm);
   }
 }
 
@@ -499,7 +517,7 @@ row_map_flat_kernel(const RowMapParams p) {
 // length loads per 8-byte element are still too many instructions.  A CTA owns 2048 consecutive
 // destination vectors = a run of consecutive sequences; their offsets are staged once in shared memory
 // (tile-relative, 32-bit), and every thread needs one 32-bit division by a CTA-uniform constant.
-template <typename V>
+template <typename V, int SRC>
 __global__ void __launch_bounds__(kTileThreads)
 row_map_padded_kernel(const RowMapParams p) {
   __shared__ int s_rel[kTileCap];            // off[i0 + k] - off[i0]; clamped only beyond the tile's reach
@@ -524,7 +542,8 @@ row_map_padded_kernel(const RowMapParams p) {
   const bool one_seq = wrv64 > (int64_t)(1u << 30);
   const uint32_t wrv = one_seq ? 1u : (uint32_t)wrv64;
   const uint32_t head = one_seq ? 0u : (uint32_t)head64;
-  const uint32_t width = (uint32_t)(p.d.width < (1ll << 31) ? p.d.width : (1ll << 31) - 1);
+  const uint32_t width = (uint32_t)(p.d.width < (1ll << 30) ? p.d.width : (1ll << 30));
+  const bool right_dst = p.d.layout == RUA_RIGHT;
 
   const V* __restrict__ src = reinterpret_cast<const V*>(p.src);
   V* __restrict__ dst = reinterpret_cast<V*>(p.dst) + e0;
@@ -543,19 +562,27 @@ row_map_padded_kernel(const RowMapParams p) {
         t = (uint32_t)(rem / rv);
         c = (uint32_t)(rem - (int64_t)t * rv);
       } else {
-        const uint32_t x = head + (uint32_t)e;
-        q = x / wrv;
+        const uint32_t x = head + (uint32_t)e;             // < 2^31: head < wrv <= 2^30, e < 2048
+        q = fast_div(x, p.div_wrv_m, p.div_wrv_s);
         const uint32_t rem = x - q * wrv;
-        if (rv == 1) { t = rem; c = 0; } else { t = rem / rv; c = rem - t * rv; }
+        if (rv == 1) { t = rem; c = 0; } else { t = fast_div(rem, p.div_rv_m, p.div_rv_s); c = rem - t * rv; }
       }
       col[r] = c;
-      const int64_t base_len = (int64_t)s_rel[q + 1] - (int64_t)s_rel[q];   // exact unless >= 2^30 (then > width anyway)
-      const int64_t ld = side_len(p.d, base_len);
-      int64_t td = t;
-      if (p.d.layout == RUA_RIGHT) td -= ((int64_t)width - ld);
       int64_t sr = kPadRow;
-      if (td >= 0 && td < ld) sr = source_row(p, i0 + q, td, base_len);
-      if (sr == kPadRow && p.pad_mode == RUA_PAD_ROW0) sr = 0;
+      if (SRC == kGenericSrc) {
+        const int64_t base_len = (int64_t)s_rel[q + 1] - (int64_t)s_rel[q];   // exact unless >= 2^30 (then > width anyway)
+        const int64_t ld = side_len(p.d, base_len);
+        int64_t td = t;
+        if (p.d.layout == RUA_RIGHT) td -= ((int64_t)width - ld);
+        if (td >= 0 && td < ld) sr = source_row(p, i0 + q, td, base_len);
+        if (sr == kPadRow && p.pad_mode == RUA_PAD_ROW0) sr = 0;
+      } else {                                   // conversions: 32-bit, branch-free up to the validity test
+        const int sq = s_rel[q];
+        const int len = s_rel[q + 1] - sq;       // >= 2^30 only when it exceeds the width anyway
+        const int td = (int)t - (right_dst ? (int)width - len : 0);
+        if (td >= 0 && td < len)
+          sr = SRC == RUA_CAT ? base0 + sq + td : simple_source_row<SRC>(p, i0 + q, td, len);
+      }
       srow[r] = sr;
     }
   }
@@ -652,7 +679,7 @@ static bool transpose_applies(const RowMapParams& p, int64_t* grid_y) {
 }
 
 template <typename V>
-static void launch_narrow(const RowMapParams& p, int64_t rows, cudaStream_t st) {
+static void launch_narrow(RowMapParams& p, int64_t rows, cudaStream_t st) {
   int64_t gy = 0;
   if (transpose_applies(p, &gy)) {
     dim3 grid((unsigned)ceil_div(p.rg.B, 32), (unsigned)gy);
@@ -663,9 +690,33 @@ static void launch_narrow(const RowMapParams& p, int64_t rows, cudaStream_t st) 
   const int64_t blocks = ceil_div(rows * p.row_vecs, kTileVecs);
   const bool indexed = p.gather_index || p.scatter_index;
   const bool searched = !indexed && (p.d.layout == RUA_CAT || p.d.layout == RUA_PACK);
-  if (searched) row_map_tile_kernel<V><<<(unsigned)blocks, kTileThreads, 0, st>>>(p);
-  else if (!indexed) row_map_padded_kernel<V><<<(unsigned)blocks, kTileThreads, 0, st>>>(p);
-  else row_map_flat_kernel<V><<<(unsigned)blocks, kTileThreads, 0, st>>>(p);
+  // the 12 conversions (identity token map, untransformed lengths, plain fill) run source-specialised code
+  const bool simple = !indexed && p.tmap == RUA_MAP_SHIFT && p.tmap_arg == 0 && p.pad_mode == RUA_PAD_FILL &&
+                      p.s.len_xform == RUA_LEN_SAME && p.d.len_xform == RUA_LEN_SAME;
+  const int srck = simple ? p.s.layout : kGenericSrc;
+  const unsigned nb = (unsigned)blocks;
+  if (searched) {
+    switch (srck) {
+      case RUA_CAT: row_map_tile_kernel<V, RUA_CAT><<<nb, kTileThreads, 0, st>>>(p); break;
+      case RUA_LEFT: row_map_tile_kernel<V, RUA_LEFT><<<nb, kTileThreads, 0, st>>>(p); break;
+      case RUA_RIGHT: row_map_tile_kernel<V, RUA_RIGHT><<<nb, kTileThreads, 0, st>>>(p); break;
+      case RUA_PACK: row_map_tile_kernel<V, RUA_PACK><<<nb, kTileThreads, 0, st>>>(p); break;
+      default: row_map_tile_kernel<V, kGenericSrc><<<nb, kTileThreads, 0, st>>>(p); break;
+    }
+  } else if (!indexed) {
+    const int64_t wrv = p.d.width * p.row_vecs;
+    const FastDiv a = FastDiv::make((uint64_t)(wrv > (1ll << 30) ? 1 : wrv)), b = FastDiv::make((uint64_t)p.row_vecs);
+    p.div_wrv_m = a.m; p.div_wrv_s = a.s; p.div_rv_m = b.m; p.div_rv_s = b.s;
+    switch (srck) {
+      case RUA_CAT: row_map_padded_kernel<V, RUA_CAT><<<nb, kTileThreads, 0, st>>>(p); break;
+      case RUA_LEFT: row_map_padded_kernel<V, RUA_LEFT><<<nb, kTileThreads, 0, st>>>(p); break;
+      case RUA_RIGHT: row_map_padded_kernel<V, RUA_RIGHT><<<nb, kTileThreads, 0, st>>>(p); break;
+      case RUA_PACK: row_map_padded_kernel<V, RUA_PACK><<<nb, kTileThreads, 0, st>>>(p); break;
+      default: row_map_padded_kernel<V, kGenericSrc><<<nb, kTileThreads, 0, st>>>(p); break;
+    }
+  } else {
+    row_map_flat_kernel<V><<<nb, kTileThreads, 0, st>>>(p);
+  }
 }
 
 static int launch_row_map(RowMapParams& p, int64_t row_bytes, int64_t rows, cudaStream_t st) {

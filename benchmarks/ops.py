@@ -172,7 +172,8 @@ def cfg5(results, reps):
     row(results, 5, 'C.offsets', 16 * b, n, lambda: c.offsets(), reps,
         aten=lambda: torch.cumsum(lc, 0).roll(1))
     row(results, 5, 'C.bmask', b * t + 8 * b, n, lambda: c.bmask(), reps)
-    row(results, 5, 'C.mask(long)', b * t * 8 + 8 * b, n, lambda: c.mask(-1, 2, torch.long), reps)
+    row(results, 5, 'C.mask(long)', b * t * 8 + 8 * b, n, lambda: c.mask(-1, 2, torch.long), reps,
+        aten=lambda: torch.full((b, t), 2, dtype=torch.long, device='cuda'))   # write-only ceiling: a plain fill
     row(results, 5, 'C.ptr', 16 * n + 8 * b, n, lambda: c.ptr(), reps,
         aten=lambda: torch.repeat_interleave(lc, output_size=n))
     row(results, 5, 'P.ptr', 16 * n + 8 * b, n, lambda: p.ptr(), reps)

@@ -7,6 +7,8 @@
 // The reference builds these from repeat_interleave (each an internal cumsum + a .item() sync),
 // arange, new_full and index_put_.  Here every output element is a closed form of (segment, within)
 // and is stored once with 16-byte coalesced stores.  HBM-write bound.
+#include <cstdlib>
+
 #include "common.cuh"
 #include "tile_decode.cuh"
 
@@ -27,55 +29,77 @@ template <typename E> __device__ __forceinline__ unsigned long long replicate64(
   return x;
 }
 
+constexpr int kMaskIters = 4;   // 32-byte spans per thread (a CTA writes 32 KB: fewer, fatter CTAs than one span per thread)
+
 template <typename E>
 __global__ void __launch_bounds__(256)
 mask_kernel(const int64_t* __restrict__ len, int64_t B, int64_t W, E zero, E one, E* __restrict__ out, int wide) {
-  constexpr int K = 32 / sizeof(E);      // elements per thread
+  constexpr int K = 32 / sizeof(E);      // elements per span
   constexpr int EPW = 8 / sizeof(E);     // elements per 64-bit word
   const int64_t total = B * W;
-  const int64_t g0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * K;
-  if (g0 >= total) return;
-  int64_t i, t;
-  if (total < (1ll << 31)) {
-    uint32_t q = (uint32_t)g0 / (uint32_t)W;
-    i = q;
-    t = (uint32_t)g0 - q * (uint32_t)W;
-  } else {
-    i = g0 / W;
-    t = g0 - i * W;
-  }
-  int64_t li = __ldg(len + i);
-  union { unsigned long long w[4]; uint4 v[2]; E e[K]; } u;
-  if (t + K <= W) {
-    const int64_t rest = li - t;
-    const int ones = rest <= 0 ? 0 : (rest >= K ? K : (int)rest);   // leading `one`s of this span
-    const unsigned long long ow = replicate64<E>(one), zw = replicate64<E>(zero);
+  const unsigned long long ow = replicate64<E>(one), zw = replicate64<E>(zero);
+  // all length loads first: the stores below are asm volatile and would serialise load -> store -> load
+  int64_t gs[kMaskIters], is[kMaskIters], ts[kMaskIters], ls[kMaskIters];
 #pragma unroll
-    for (int w = 0; w < 4; ++w) {
-      const int n1 = ones - w * EPW;
-      const unsigned long long m = n1 >= EPW ? ~0ull : (n1 <= 0 ? 0ull : ((1ull << (n1 * 8 * (int)sizeof(E) & 63)) - 1ull));
-      u.w[w] = (ow & m) | (zw & ~m);
-    }
-  } else {
-#pragma unroll
-    for (int k = 0; k < K; ++k) {
-      u.e[k] = t < li ? one : zero;
-      if (++t == W) {
-        t = 0;
-        ++i;
-        li = i < B ? __ldg(len + i) : 0;
+  for (int it = 0; it < kMaskIters; ++it) {
+    const int64_t g0 = (((int64_t)blockIdx.x * kMaskIters + it) * blockDim.x + threadIdx.x) * K;
+    gs[it] = g0;
+    int64_t i = 0, t = 0;
+    if (g0 < total) {
+      if (total < (1ll << 31)) {
+        uint32_t q = (uint32_t)g0 / (uint32_t)W;
+        i = q;
+        t = (uint32_t)g0 - q * (uint32_t)W;
+      } else {
+        i = g0 / W;
+        t = g0 - i * W;
       }
     }
+    is[it] = i;
+    ts[it] = t;
+    ls[it] = g0 < total ? __ldg(len + i) : 0;
   }
-  if (g0 + K <= total) {
-    if (wide) {
-      asm volatile("st.global.cs.v4.b64 [%0], {%1, %2, %3, %4};" ::"l"(out + g0), "l"(u.w[0]), "l"(u.w[1]), "l"(u.w[2]), "l"(u.w[3]) : "memory");
-    } else {
-      __stcs(reinterpret_cast<uint4*>(out + g0), u.v[0]);
-      __stcs(reinterpret_cast<uint4*>(out + g0) + 1, u.v[1]);
+#pragma unroll
+  for (int it = 0; it < kMaskIters; ++it) {
+    const int64_t g0 = gs[it];
+    if (g0 >= total) return;
+    int64_t i = is[it], t = ts[it], li = ls[it];
+    unsigned long long w0 = 0, w1 = 0, w2 = 0, w3 = 0;   // the 32 output bytes, in registers (no local-memory union)
+    if (t + K <= W) {
+      const int64_t rest = li - t;
+      const int ones = rest <= 0 ? 0 : (rest >= K ? K : (int)rest);   // leading `one`s of this span
+      auto word = [&](int w) -> unsigned long long {
+        const int n1 = ones - w * EPW;
+        const unsigned long long m = n1 >= EPW ? ~0ull : (n1 <= 0 ? 0ull : ((1ull << (n1 * 8 * (int)sizeof(E) & 63)) - 1ull));
+        return (ow & m) | (zw & ~m);
+      };
+      w0 = word(0); w1 = word(1); w2 = word(2); w3 = word(3);
+    } else {                                              // the span crosses a row end: element by element
+#pragma unroll
+      for (int k = 0; k < K; ++k) {
+        const unsigned long long e = (unsigned long long)(t < li ? one : zero) << ((k % EPW) * 8 * (int)sizeof(E) & 63);
+        if (k / EPW == 0) w0 |= e; else if (k / EPW == 1) w1 |= e; else if (k / EPW == 2) w2 |= e; else w3 |= e;
+        if (++t == W) {
+          t = 0;
+          ++i;
+          li = i < B ? __ldg(len + i) : 0;
+        }
+      }
     }
-  } else {
-    for (int k = 0; g0 + k < total; ++k) out[g0 + k] = u.e[k];
+    if (g0 + K <= total) {
+      if (wide) {
+        asm volatile("st.global.cs.v4.b64 [%0], {%1, %2, %3, %4};" ::"l"(out + g0), "l"(w0), "l"(w1), "l"(w2), "l"(w3) : "memory");
+      } else {
+        __stcs(reinterpret_cast<ulonglong2*>(out + g0), make_ulonglong2(w0, w1));
+        __stcs(reinterpret_cast<ulonglong2*>(out + g0) + 1, make_ulonglong2(w2, w3));
+      }
+    } else {
+#pragma unroll
+      for (int k = 0; k < K; ++k) {
+        const unsigned long long w = k / EPW == 0 ? w0 : (k / EPW == 1 ? w1 : (k / EPW == 2 ? w2 : w3));
+        if (g0 + k < total) out[g0 + k] = (E)(w >> ((k % EPW) * 8 * (int)sizeof(E) & 63));
+      }
+    }
   }
 }
 
@@ -179,7 +203,7 @@ int rua_mask(const int64_t* len, int64_t B, int64_t W, const void* zero_host, co
   cudaStream_t st = (cudaStream_t)stream;
   const int64_t total = B * W;
   const int64_t per = 32 / elem_bytes;
-  const int64_t blocks = ceil_div(ceil_div(total, per), 256);
+  const int64_t blocks = ceil_div(ceil_div(total, per), 256 * kMaskIters);
   const int wide = ((uintptr_t)out & 31u) == 0;
   if (blocks >= (1ll << 31)) return RUA_ERR_UNSUPPORTED;
   switch (elem_bytes) {

@@ -246,7 +246,7 @@ static RedPlan plan_reduce(int64_t N, int64_t H, int32_t dtype, int32_t op, cons
   p.dtype = dtype;
   if (flat_supported(dtype, H)) {  // narrow rows: rows map to lanes (reduce_flat.cu)
     p.flat = true;
-    p.vector_loads = (((uintptr_t)data) & 15u) == 0;
+    p.vector_loads = (((uintptr_t)data) & 31u) == 0 ? 2 : ((((uintptr_t)data) & 15u) == 0 ? 1 : 0);   // 256- / 128-bit loads
     p.vec = 1;
     p.threads = 32;
     p.col_tiles = 1;
@@ -289,7 +289,7 @@ static int run_reduce(const RedPlan& p, const void* data, const int64_t* ridx, c
     if (p.col_tiles > 65535) return RUA_ERR_UNSUPPORTED;
     dim3 grid((unsigned)p.chunks, (unsigned)p.col_tiles);
     if (p.flat) {
-      rc = flat_launch(p.dtype, H, OP, data, ridx, off, N, S, out, head, tail, tail_seg, hdr, p.vector_loads && !ridx, p.chunks, st);
+      rc = flat_launch(p.dtype, H, OP, data, ridx, off, N, S, out, head, tail, tail_seg, hdr, ridx ? 0 : p.vector_loads, p.chunks, st);
       if (rc) return rc;
     } else {
       if (ridx)

@@ -13,6 +13,7 @@
 // warp totals.  Pieces of segments that cross tile boundaries go to the same head/tail scratch as in
 // reduce.cu and are merged in tile order by segreduce_span_kernel: deterministic, no float atomics.
 #include "reduce_common.cuh"
+#include "tile_decode.cuh"
 
 namespace rua {
 
@@ -38,6 +39,18 @@ __device__ __forceinline__ State<A, HE, OP> flat_shfl_up(const State<A, HE, OP>&
   return o;
 }
 
+// rows per thread: G = rows per 128-bit load, kLoads loads -> GL = 4, 8 or 16 consecutive rows.  The fixed cost
+// per thread (segment lookup, block-wide segmented scan, emit) is what made this kernel issue-bound at one
+// load per thread (119 instructions per row at fp32 H = 1); it is now amortised over up to 16 rows.
+template <typename T, int HE>
+struct FlatShape {
+  static constexpr int E = 16 / (int)sizeof(T);
+  static constexpr int G = E / HE;
+  static constexpr int kLoads = G * 4 <= 16 ? 4 : 16 / G;
+  static constexpr int GL = G * kLoads;
+  static constexpr int R = kFlatThreads * GL;   // rows per tile
+};
+
 template <typename T, int HE, int OP>
 __global__ void __launch_bounds__(kFlatThreads)
 segreduce_flat_kernel(const T* __restrict__ data, const int64_t* __restrict__ ridx, const int64_t* __restrict__ off,
@@ -47,63 +60,75 @@ segreduce_flat_kernel(const T* __restrict__ data, const int64_t* __restrict__ ri
                       int vector_loads) {
   using A = typename Store<T>::Acc;
   using St = State<A, HE, OP>;
+  using Shape = FlatShape<T, HE>;
   constexpr bool kFast = sizeof(T) == 2;
-  constexpr int E = 16 / sizeof(T);            // elements per 128-bit load
-  constexpr int G = E / HE;                    // rows per thread
-  constexpr int R = kFlatThreads * G;          // rows per tile
-  constexpr int kCap = R + 2;
+  constexpr int E = Shape::E;                  // elements per 128-bit load
+  constexpr int G = Shape::G;                  // rows per load
+  constexpr int L = Shape::kLoads;             // loads per thread
+  constexpr int GL = Shape::GL;                // rows per thread
+  constexpr int R = Shape::R;                  // rows per tile
   constexpr int P = OpInfo<OP>::kParts;
   constexpr int SV = OpInfo<OP>::kIsLse ? 2 * HE : HE;   // scalars per partial state
-  __shared__ int s_rel[kCap];
-  __shared__ int64_t s_bounds[2];
+  static_assert(kFlatThreads == kDecThreads, "tile_decode.cuh assumes 256 threads");
+  __shared__ TileDecodeSmemT<GL> sm;
   __shared__ int s_wkey[kFlatWarps];
   __shared__ A s_wval[kFlatWarps][SV];
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int64_t tile = blockIdx.x;
   const int64_t row0 = tile * R;
-  const int nrows = (int)(row0 + R < N ? R : N - row0);
-
-  // ---- which segments intersect the tile ------------------------------------------------------
-  GlobalOff g{off};
-  if (warp == 0) {
-    int64_t a = warp_owner_search(g, S, row0, lane);
-    if (lane == 0) s_bounds[0] = a;
-  } else if (warp == 1) {
-    int64_t b = warp_owner_search(g, S, row0 + nrows - 1, lane);
-    if (lane == 0) s_bounds[1] = b;
+  // rows past the last segment (sum of sizes < N) belong to nobody and are not reduced
+  const int64_t covered = __ldg(off + S) < N ? __ldg(off + S) : N;
+  const int nrows = (int)(row0 + R < covered ? R : covered - row0);
+  if (nrows <= 0) {                             // CTA-uniform
+    if (tid == 0) tail_seg[tile] = -1;
+    return;
   }
-  __syncthreads();
-  const int64_t first = s_bounds[0], last = s_bounds[1];
-  const int64_t cnt64 = last - first + 2;
-  const bool staged = cnt64 <= kCap;
-  const int cnt = (int)(cnt64 < (1 << 30) ? cnt64 : (1 << 30));
+
+  // ---- the thread's GL rows are requested FIRST (256-bit loads: one full sector per lane), so that the DRAM
+  // latency overlaps the tile decode and its barriers -----------------------------------------------------
+  const int tr0 = tid * GL;                     // tile-relative first row of this thread
+  const bool vec = vector_loads && row0 + tr0 + GL <= N && tr0 < nrows;   // rows beyond `nrows` but inside N are ignored
+  uint4 raw[L];
+  if (vec) {
+    const T* base = data + (row0 + tr0) * HE;
+    if (vector_loads == 2) {
+#pragma unroll
+      for (int l = 0; l < L; l += 2)
+        asm volatile("ld.global.nc.L1::no_allocate.v4.b64 {%0, %1, %2, %3}, [%4];"
+                     : "=l"(*reinterpret_cast<unsigned long long*>(&raw[l].x)), "=l"(*reinterpret_cast<unsigned long long*>(&raw[l].z)),
+                       "=l"(*reinterpret_cast<unsigned long long*>(&raw[l + 1].x)), "=l"(*reinterpret_cast<unsigned long long*>(&raw[l + 1].z))
+                     : "l"(base + l * E));
+    } else {
+#pragma unroll
+      for (int l = 0; l < L; ++l) raw[l] = __ldg(reinterpret_cast<const uint4*>(base + l * E));
+    }
+  }
+
+  // ---- which segment owns each row of the tile (tile_decode.cuh) ---------------------------------
+  GlobalOff g{off};
+  const TileDecode dec = tile_decode<GL>(g, S, row0, nrows, sm);
+  const bool staged = dec.staged;
+  const int64_t first = dec.first;
   // tile-relative, clamped offsets: rel(k) = off[first + k] - row0 in [-1, R + 1]
   auto rel = [&](int k) -> int {
-    if (staged) return s_rel[k];
+    if (staged) return sm.rel[k];
     int64_t d = __ldg(off + first + k) - row0;
     return d < -1 ? -1 : (d > R + 1 ? R + 1 : (int)d);
   };
-  if (staged) {
-    for (int k = tid; k < cnt; k += kFlatThreads) {
-      int64_t d = __ldg(off + first + k) - row0;
-      s_rel[k] = d < -1 ? -1 : (d > R + 1 ? R + 1 : (int)d);
-    }
-  }
-  __syncthreads();
 
-  // ---- thread-local reduction of G consecutive rows, cut at segment boundaries ------------------
-  const int tr0 = tid * G;                      // tile-relative first row of this thread
-  A x[E];
-  if (tr0 + G <= nrows && vector_loads) {
-    uint4 raw = __ldcs(reinterpret_cast<const uint4*>(data + (row0 + tr0) * HE));
-    Store<T>::unpack(raw, x);
-  } else {
+  // ---- thread-local reduction of GL consecutive rows, cut at segment boundaries -----------------
+  int sg[GL];                                   // owning segment (relative to `first`) of each row
+  if (staged) {
 #pragma unroll
-    for (int k = 0; k < E; ++k) {
-      const int64_t row = row0 + tr0 + k / HE;                       // optional row gather (scatter_*)
-      x[k] = tr0 + k / HE < nrows ? Store<T>::to_acc(data[(ridx ? __ldg(ridx + row) : row) * HE + k % HE]) : A(0);
+    for (int q = 0; q < GL / 4; ++q) {
+      const int4 v = reinterpret_cast<const int4*>(sm.seg)[tid * (GL / 4) + q];
+      sg[4 * q] = v.x; sg[4 * q + 1] = v.y; sg[4 * q + 2] = v.z; sg[4 * q + 3] = v.w;
     }
+  } else {                                      // runs of empty segments overflowed the stage: search per row
+#pragma unroll
+    for (int k = 0; k < GL; ++k)
+      sg[k] = tr0 + k < nrows ? (int)(owner_search(g, S, row0 + tr0 + k) - first) : 0;
   }
 
   A ext = OP == RUA_MIN ? -inf_of<A>() : inf_of<A>();
@@ -113,17 +138,8 @@ segreduce_flat_kernel(const T* __restrict__ data, const int64_t* __restrict__ ri
   firstRun.reset();
   int firstLo = -1;                             // the first CLOSED run of this thread (may need a carry-in)
   int closed = 0;
-  int lo = 0, seg_end = 0;
+  int lo = -1;                                  // segment of the run being accumulated
   bool have = false;                            // acc holds at least one row
-  if (tr0 < nrows) {
-    int a = 0, b = cnt - 1;                     // segment of the first row: search over the staged offsets
-    while (b - a > 1) {
-      const int mid = (a + b) >> 1;
-      if (rel(mid) <= tr0) a = mid; else b = mid;
-    }
-    lo = a;
-    seg_end = rel(lo + 1);
-  }
   auto seg_len = [&](int l) -> int64_t { return __ldg(off + first + l + 1) - __ldg(off + first + l); };
   auto close_run = [&]() {
     if (closed == 0) {
@@ -143,27 +159,39 @@ segreduce_flat_kernel(const T* __restrict__ data, const int64_t* __restrict__ ri
     have = false;
   };
 #pragma unroll
-  for (int k = 0; k < G; ++k) {
-    const int row = tr0 + k;
-    if (row < nrows) {
-      if (row >= seg_end) {
-        if (have) close_run();
-        while (row >= seg_end && lo + 2 < cnt) {  // next non-empty segment
-          ++lo;
-          seg_end = rel(lo + 1);
-        }
-        if (row >= seg_end) break;  // rows past the last segment (sum of sizes < N): not reduced
-      }
-      acc.template add<kFast>(&x[k * HE]);
-      have = true;
-      if (OpInfo<OP>::kNeedsExt) {
+  for (int l = 0; l < L; ++l) {
+    const int rb = tr0 + l * G;                 // first row of this load
+    if (rb < nrows) {
+      A x[E];
+      if (vec) {
+        Store<T>::unpack(raw[l], x);
+      } else {
 #pragma unroll
-        for (int h = 0; h < HE; ++h) ext = OP == RUA_MIN ? max_num(ext, x[k * HE + h]) : min_num(ext, x[k * HE + h]);
+        for (int k = 0; k < E; ++k) {
+          const int64_t row = row0 + rb + k / HE;                      // optional row gather (scatter_*)
+          x[k] = rb + k / HE < nrows ? Store<T>::to_acc(data[(ridx ? __ldg(ridx + row) : row) * HE + k % HE]) : A(0);
+        }
+      }
+#pragma unroll
+      for (int k = 0; k < G; ++k) {
+        if (rb + k < nrows) {
+          const int s_k = sg[l * G + k];
+          if (s_k != lo) {
+            if (have) close_run();
+            lo = s_k;
+          }
+          acc.template add<kFast>(&x[k * HE]);
+          have = true;
+          if (OpInfo<OP>::kNeedsExt) {
+#pragma unroll
+            for (int h = 0; h < HE; ++h) ext = OP == RUA_MIN ? max_num(ext, x[k * HE + h]) : min_num(ext, x[k * HE + h]);
+          }
+        }
       }
     }
   }
-  const int my_end = tr0 + G < nrows ? tr0 + G : nrows;   // one past this thread's last row
-  if (have && seg_end == my_end) close_run();             // the segment ends exactly with this thread
+  const int my_end = tr0 + GL < nrows ? tr0 + GL : nrows;  // one past this thread's last row
+  if (have && rel(lo + 1) == my_end) close_run();         // the segment ends exactly with this thread
   // what is left in `acc` (if `have`) is an OPEN run of segment first+lo, continuing to the right
   int key = have ? lo : -1;
   St val = acc;
@@ -252,7 +280,7 @@ segreduce_flat_kernel(const T* __restrict__ data, const int64_t* __restrict__ ri
       store_partial<A, HE, OP>(head + tile * P * HE, HE, 0, v);
     }
   }
-  const int last_thread = (nrows - 1) / G;
+  const int last_thread = (nrows - 1) / GL;
   if (tid == last_thread) {
     int64_t spans = -1;
     if (key >= 0) {  // the tile ends inside a segment
@@ -330,9 +358,10 @@ bool flat_supported(int32_t dtype, int64_t H) {
   return H >= 1 && H <= e && (H & (H - 1)) == 0;
 }
 
-int flat_rows_per_tile(int32_t dtype, int64_t H) {
+int flat_rows_per_tile(int32_t dtype, int64_t H) {   // == FlatShape<T, H>::R
   const int e = dtype == RUA_F32 ? 4 : (dtype == RUA_F64 ? 2 : 8);
-  return kFlatThreads * (e / (int)H);
+  const int g = e / (int)H;
+  return kFlatThreads * g * (g * 4 <= 16 ? 4 : 16 / g);
 }
 
 int flat_launch(int32_t dtype, int64_t H, int32_t op, const void* data, const int64_t* ridx, const int64_t* off,

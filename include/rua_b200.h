@@ -212,6 +212,14 @@ int rua_segment_reduce_gather(const void* data, const int64_t* row_index, const 
                               int64_t S, int64_t H, int32_t dtype, int32_t op, void* out, void* ws,
                               size_t ws_bytes, rua_stream_t stream);
 
+/* PARITY MODE for sum / mean / prod: the reference's order of operations replayed exactly -- per (segment,
+ * column) strictly left to right in the STORAGE dtype with one rounding per step, mean divides by the length
+ * converted to the storage dtype (what torch.segment_reduce computes for torchrua/reduce.py:44-53; SURVEY.md
+ * 8c hazard 2).  Bit-identical to the reference for fp32 / fp64 / fp16 / bf16.  No workspace.  Other ops return
+ * RUA_ERR_UNSUPPORTED (max / min are bit-exact in rua_segment_reduce already). */
+int rua_segment_reduce_strict(const void* data, const int64_t* off, int64_t N, int64_t S, int64_t H,
+                              int32_t dtype, int32_t op, void* out, rua_stream_t stream);
+
 /* backward twin (ATen SegmentReduceBackward0 semantics): sum -> broadcast, mean ->
  * broadcast / len, max/min -> split evenly among ties, prod -> grad*out/x (exact when x != 0, else
  * product of the others), logsumexp -> softmax weights. */

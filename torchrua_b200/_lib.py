@@ -59,6 +59,8 @@ SIGNATURES = {
     'rua_segment_reduce_workspace_bytes': (c_size_t, [c_int64, c_int64, c_int64, c_int32, c_int32]),
     'rua_segment_reduce': (c_int32, [c_void_p, c_void_p, c_int64, c_int64, c_int64, c_int32, c_int32, c_void_p,
                                      c_void_p, c_size_t, c_void_p]),
+    'rua_segment_reduce_strict': (c_int32, [c_void_p, c_void_p, c_int64, c_int64, c_int64, c_int32, c_int32, c_void_p,
+                                            c_void_p]),
     'rua_segment_reduce_backward_workspace_bytes': (c_size_t, [c_int64, c_int64, c_int64, c_int32, c_int32]),
     'rua_segment_reduce_backward': (c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int64,
                                               c_int32, c_int32, c_void_p, c_void_p, c_size_t, c_void_p]),

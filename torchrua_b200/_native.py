@@ -548,6 +548,31 @@ def emit_ptr(off: Tensor, n: int, relabel: Optional[Tensor] = None, want_which=T
 # ------------------------------------------------------------------------------------------------
 # K4: segment reduce (+ autograd)
 # ------------------------------------------------------------------------------------------------
+# parity mode (SURVEY.md 8c hazard 2): sum / mean / prod replay torch.segment_reduce's order of operations
+# (sequential, one rounding to the storage dtype per step) and match the reference bit for bit
+STRICT_REDUCTIONS = False
+_STRICT_OPS = (_lib.SUM, _lib.MEAN, _lib.PROD)
+
+
+class strict_reductions:
+    """``with strict_reductions():`` -- segment_sum / segment_mean / segment_prod (and .seg(...) through them)
+    return exactly the bits of the reference; the default fast kernels stay within the stated tolerance of it
+    (fp32 accumulation, one rounding) and are closer to the true value for 16-bit data."""
+
+    def __init__(self, enabled: bool = True):
+        self.enabled = enabled
+
+    def __enter__(self):
+        global STRICT_REDUCTIONS
+        self.prev, STRICT_REDUCTIONS = STRICT_REDUCTIONS, self.enabled
+        return self
+
+    def __exit__(self, *exc):
+        global STRICT_REDUCTIONS
+        STRICT_REDUCTIONS = self.prev
+        return False
+
+
 def _reduce_raw(data: Tensor, off: Tensor, S: int, op: int) -> Tensor:
     lib = _lib.load()
     if data.dtype not in _DTYPES:
@@ -563,6 +588,11 @@ def _reduce_raw(data: Tensor, off: Tensor, S: int, op: int) -> Tensor:
     if out.numel() == 0:
         return out
     dt = _DTYPES[data.dtype]
+    if STRICT_REDUCTIONS and op in _STRICT_OPS:
+        with _on(data.device):
+            _lib.check(lib.rua_segment_reduce_strict(_ptr(data), off.data_ptr(), N, S, H, dt, op, out.data_ptr(),
+                                                     _stream()), 'rua_segment_reduce_strict')
+        return out
     with _on(data.device):
         nbytes = lib.rua_segment_reduce_workspace_bytes(N, S, H, dt, op)
         ws = torch.empty(nbytes, dtype=torch.uint8, device=data.device)

@@ -9,7 +9,7 @@ import torch
 
 from torchrua_b200 import _native
 from torchrua_b200._lib import CAT, LEN_CONST, MAP_REV, MAP_SHIFT, PAD_FILL, PAD_WRAP
-from torchrua_b200._native import MapSpec, SideSpec
+from torchrua_b200._native import MapSpec, SideSpec, strict_reductions  # noqa: F401  (extension: parity mode)
 from torchrua_b200.layout import T
 
 

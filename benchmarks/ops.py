@@ -106,6 +106,15 @@ def cfg2(results, reps):
             lc = lens.cuda()
             aten = lambda fn=fn, lc=lc: torch.segment_reduce(data, fn, lengths=lc, unsafe=True)
         row(results, 2, f'segment_{fn}', nd + b * d + 8 * b, n, lambda f=f: f(data, c.token_sizes), reps, aten)
+    # parity mode: the reference's sequential, per-step-rounded accumulation (bit-identical to torch.segment_reduce)
+    from torchrua_b200.reduce import strict_reductions
+
+    def strict_sum():
+        with strict_reductions():
+            return rua.segment_sum(data, c.token_sizes)
+    lc2 = lens.cuda()
+    row(results, 2, 'segment_sum (strict mode)', nd + b * d + 8 * b, n, strict_sum, reps,
+        lambda: torch.segment_reduce(data, 'sum', lengths=lc2, unsafe=True))
     # scatter_* ("next" row 8f-1): the same rows in a random order, reduced by an unsorted index
     perm = torch.randperm(n, device='cuda')
     idx = torch.repeat_interleave(torch.arange(b, device='cuda'), lens.cuda())[perm]

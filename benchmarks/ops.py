@@ -106,6 +106,23 @@ def cfg2(results, reps):
             lc = lens.cuda()
             aten = lambda fn=fn, lc=lc: torch.segment_reduce(data, fn, lengths=lc, unsafe=True)
         row(results, 2, f'segment_{fn}', nd + b * d + 8 * b, n, lambda f=f: f(data, c.token_sizes), reps, aten)
+    # constructors from a list of 4096 tensors: host-side metadata + one multi-source kernel
+    from torch.nn.utils.rnn import pack_sequence, pad_sequence
+    pieces = list(torch.split(data, lens.tolist()))
+    row(results, 2, 'L.new(list of 4096)', nd + btd, n, lambda: rua.L.new(pieces), max(3, reps // 3),
+        aten=lambda: pad_sequence(pieces, batch_first=True))
+    row(results, 2, 'P.new(list of 4096)', 2 * nd, n, lambda: rua.P.new(pieces), max(3, reps // 3),
+        aten=lambda: pack_sequence(pieces, enforce_sorted=False))
+    row(results, 2, 'C.new(list of 4096)', 2 * nd, n, lambda: rua.C.new(pieces), max(3, reps // 3),
+        aten=lambda: torch.cat(pieces, dim=0))
+    del pieces
+    big = list(torch.split(data, [n // 64] * 63 + [n - 63 * (n // 64)]))     # few large tensors: the multi-source kernel
+    tb = n // 64 + (n - 63 * (n // 64) - n // 64)
+    row(results, 2, 'L.new(list of 64 x 33 MB)', nd + 64 * max(n // 64, tb) * d, n, lambda: rua.L.new(big), reps,
+        aten=lambda: pad_sequence(big, batch_first=True))
+    row(results, 2, 'P.new(list of 64 x 33 MB)', 2 * nd, n, lambda: rua.P.new(big), reps,
+        aten=lambda: pack_sequence(big, enforce_sorted=False))
+    del big
     # parity mode: the reference's sequential, per-step-rounded accumulation (bit-identical to torch.segment_reduce)
     from torchrua_b200.reduce import strict_reductions
 

@@ -165,6 +165,14 @@ int rua_row_map(const void* src, void* dst, int64_t row_bytes, const rua_ragged_
                 int64_t tmap_arg, int32_t pad_mode, const void* fill_host, int32_t fill_bytes,
                 rua_stream_t stream);
 
+/* constructors C/L/P/R.new(list) (torchrua/core/__init__.py:9-36): rua_row_map with an identity token map whose
+ * SOURCE is a list -- sequence i is its own contiguous (len[i], row_bytes) allocation src_list[i].  src_list is a
+ * DEVICE array of B device pointers; src_align = a power of two that divides every non-null pointer in it (the
+ * kernel picks its vector width from it).  Replaces torch.cat + conversion: every payload byte moves once. */
+int rua_row_map_list(const void* const* src_list, int32_t src_align, void* dst, int64_t row_bytes,
+                     const rua_ragged_t* ragged, const rua_side_t* dst_side, const void* fill_host,
+                     int32_t fill_bytes, rua_stream_t stream);
+
 /* dst[j] = src[index[j]] for j < n   (tensor_getitem / Z-keyed getitem, core/get.py:11-31).
  * Negative indices wrap (index + src_rows) like torch advanced indexing. */
 int rua_gather_rows(const void* src, int64_t src_rows, const int64_t* index, int64_t n,

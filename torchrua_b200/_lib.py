@@ -51,6 +51,8 @@ SIGNATURES = {
                                  c_void_p]),
     'rua_row_map': (c_int32, [c_void_p, c_void_p, c_int64, POINTER(Ragged), POINTER(Side), POINTER(Side),
                               c_int32, c_int64, c_int32, c_char_p, c_int32, c_void_p]),
+    'rua_row_map_list': (c_int32, [c_void_p, c_int32, c_void_p, c_int64, POINTER(Ragged), POINTER(Side), c_char_p,
+                                   c_int32, c_void_p]),
     'rua_gather_rows': (c_int32, [c_void_p, c_int64, c_void_p, c_int64, c_int64, c_void_p, c_void_p]),
     'rua_scatter_rows': (c_int32, [c_void_p, c_void_p, c_int64, c_int64, c_void_p, c_int64, c_void_p]),
     'rua_mask': (c_int32, [c_void_p, c_int64, c_int64, c_char_p, c_char_p, c_int32, c_void_p, c_void_p]),

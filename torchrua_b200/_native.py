@@ -459,6 +459,158 @@ def row_map(src_flat: Tensor, spec: MapSpec, fill_value=0) -> Tensor:
     return _RowMap.apply(src_flat, spec, fill)
 
 
+# ------------------------------------------------------------------------------------------------
+# constructors from lists of tensors (C/L/P/R.new): metadata on the HOST (the lengths are shapes: no device
+# sync at all), one upload, one multi-source row-map launch
+# ------------------------------------------------------------------------------------------------
+HOST_SORT_MAX_B = 1 << 16      # above this the stable sort for P.new runs on the device (K0) instead of numpy
+
+
+def ragged_from_host_lengths(lengths, device: torch.device, want_pack: bool, extra_host: Optional[Tensor] = None):
+    """Ragged for lengths known on the host (list construction).  Everything -- offsets, N, T and, for small
+    batches, the stable descending order, batch_sizes and their prefix sums -- is computed with numpy and
+    shipped in ONE pinned H2D copy; nothing is read back.  ``extra_host`` (int64) rides along in the same copy
+    (the pointer table of the list kernel) and is returned as a device view."""
+    import numpy as np
+    lens_np = np.asarray(lengths, dtype=np.int64)
+    b = int(lens_np.size)
+    n = int(lens_np.sum()) if b else 0
+    t = int(lens_np.max()) if b else 0
+    host_pack = want_pack and 0 < b <= HOST_SORT_MAX_B
+    parts = [lens_np, np.concatenate(([0], np.cumsum(lens_np)))]
+    if host_pack:
+        srt = np.argsort(-lens_np, kind='stable')
+        uns = np.empty_like(srt)
+        uns[srt] = np.arange(b, dtype=np.int64)
+        bs = (np.bincount(lens_np, minlength=t + 1)[::-1].cumsum()[::-1][1:] if t > 0 else np.zeros(0, np.int64)).astype(np.int64)
+        parts += [srt.astype(np.int64), uns, bs, np.concatenate(([0], np.cumsum(bs)))]
+    n_extra = 0 if extra_host is None else extra_host.numel()
+    sizes = [p.size for p in parts]
+    host = torch.empty(sum(sizes) + n_extra, dtype=torch.long, pin_memory=True)
+    view = host.numpy()
+    at = 0
+    for p in parts:
+        view[at:at + p.size] = p
+        at += p.size
+    if n_extra:
+        host[at:] = extra_host
+    with _on(device):
+        devbuf = host.to(device, non_blocking=True)
+    cuts, at = [], 0
+    for sz in sizes:
+        cuts.append(devbuf[at:at + sz])
+        at += sz
+    rg = Ragged(device=device, B=b, len=cuts[0], off=cuts[1], _N=n, _T=t)
+    rg._keep += [devbuf, host]         # the pinned staging buffer must outlive the asynchronous copy
+    if host_pack:
+        rg.sorted, rg.unsorted, rg.bs_dev, rg.poff = cuts[2], cuts[3], cuts[4], cuts[5]
+        rg.Tp = t
+        rg.bs_cpu = torch.from_numpy(bs.copy())
+        _cache_put(rg.unsorted, 'pack', rg)
+    elif want_pack:
+        rg.ensure_pack()
+    _cache_put(rg.len, 'len', rg)
+    return rg, (devbuf[at:] if n_extra else None)
+
+
+def _list_row_bytes(t: Tensor) -> int:
+    n = t.element_size()
+    for f in t.shape[1:]:
+        n *= f
+    return n
+
+
+_T_SIZE, _T_PTR, _T_CONTIG, _T_DEV = Tensor.size, Tensor.data_ptr, Tensor.is_contiguous, Tensor.get_device
+
+
+def _dtype_of(t):
+    return t.dtype
+
+
+def list_plan(tensors):
+    """One cheap pass over the list (this is host-bound for thousands of tensors: ~0.5 us per tensor, no per-tensor
+    Tensor objects created).  None if the multi-source kernel cannot take it (CPU tensors, mixed dtypes / devices /
+    trailing shapes): the caller then goes through torch.cat and gets ATen's promotion rules and error messages."""
+    if len(tensors) == 0 or not all(isinstance(t, Tensor) for t in tensors):
+        return None
+    t0 = tensors[0]
+    if not t0.is_cuda or t0.dim() < 1:
+        return None
+    sizes = list(map(_T_SIZE, tensors))
+    feat = sizes[0][1:]
+    if len(set(map(_dtype_of, tensors))) != 1 or len(set(map(_T_DEV, tensors))) != 1:
+        return None
+    if any(sz[1:] != feat for sz in sizes):
+        return None
+    keep = tensors
+    if not all(map(_T_CONTIG, tensors)):
+        keep = [t if t.is_contiguous() else t.contiguous() for t in tensors]
+    ptrs = list(map(_T_PTR, keep))
+    return [sz[0] for sz in sizes], ptrs, tuple(feat), keep
+
+
+def _list_forward(tensors, layout: int, fill: bytes, plan):
+    """-> (data in `layout`, Ragged, destination side)."""
+    lib = _lib.load()
+    lengths, ptrs, feat, keep = plan
+    t0 = tensors[0]
+    dev = t0.device
+    bits = 0
+    for q in ptrs:
+        bits |= q
+    align = 32
+    while bits % align:
+        align >>= 1
+    rg, ptr_dev = ragged_from_host_lengths(lengths, dev, layout == PACK, torch.tensor(ptrs, dtype=torch.long))
+    b, t, n = rg.B, rg._T, rg._N
+    if layout in (LEFT, RIGHT):
+        side, shape = SideSpec(layout, width=t, rows=b * t), (b, t) + feat
+    else:
+        side, shape = SideSpec(layout, rows=n), (n,) + feat
+    out = torch.empty(shape, dtype=t0.dtype, device=dev)
+    row_bytes = _list_row_bytes(t0)
+    if out.numel() > 0:
+        rgc, d = rg.c_struct(), side.c_struct()
+        with _on(dev):
+            _lib.check(lib.rua_row_map_list(ptr_dev.data_ptr(), align, out.data_ptr(), row_bytes, ctypes.byref(rgc),
+                                            ctypes.byref(d), fill, len(fill), _stream()), 'rua_row_map_list')
+    del keep   # contiguous temporaries (if any) are released stream-ordered by the caching allocator
+    return out, rg, side
+
+
+class _ListNew(torch.autograd.Function):
+    """list of (len_i, *feat) tensors -> data of a C / L / P / R sequence; gradients flow back to every tensor."""
+
+    @staticmethod
+    def forward(ctx, layout: int, fill: bytes, holder: list, plan, *tensors: Tensor):
+        out, rg, side = _list_forward(tensors, layout, fill, plan)
+        ctx.rg, ctx.side = rg, side
+        ctx.lengths = plan[0]
+        holder.append(rg)
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_out: Tensor):
+        rg, side = ctx.rg, ctx.side
+        g = grad_out.contiguous()
+        if side.layout != CAT:   # back to sequence-major rows: one inverse row map
+            flat = g.view((side.rows,) + tuple(g.shape[2:] if side.layout in (LEFT, RIGHT) else g.shape[1:]))
+            spec = MapSpec(rg=rg, src=side, dst=SideSpec(CAT, rows=rg.N))
+            g = _row_map_raw(flat, spec, bytes(g.element_size()), tuple(flat.shape[1:]), g.dtype, g.device)
+        return (None, None, None, None) + tuple(g.split(ctx.lengths, dim=0))
+
+
+def new_from_list(tensors, layout: int, fill_value, plan):
+    """-> (data, Ragged) of the list laid out as `layout`; one kernel, no host sync.  plan = list_plan(tensors)."""
+    fill = scalar_bytes(fill_value, tensors[0].dtype)
+    if torch.is_grad_enabled() and any(t.requires_grad for t in tensors):
+        holder = []
+        out = _ListNew.apply(layout, fill, holder, plan, *tensors)
+        return out, holder[0]
+    out, rg, _ = _list_forward(tensors, layout, fill, plan)
+    return out, rg
+
+
 class _GatherRows(torch.autograd.Function):
     @staticmethod
     def forward(ctx, src: Tensor, index: Tensor):

@@ -289,6 +289,84 @@ row_map_kernel(const RowMapParams p) {
 }
 
 // ------------------------------------------------------------------------------------------------
+// constructors (C/L/P/R.new(list_of_tensors), torchrua/core/__init__.py:9-36): the reference
+// concatenates the list (one read + one write of N*D) and then converts (another pass).  Here sequence i stays
+// in its own allocation: the destination is walked once and token (i, t) is read from src_list[i] + t * D.
+// ------------------------------------------------------------------------------------------------
+// destination row j -> (sequence, token) in the destination layout; false = padding
+__device__ __forceinline__ bool decode_dst(const RowMapParams& p, int64_t j, int64_t& i, int64_t& td, int64_t& base_len) {
+  const rua_ragged_t& rg = p.rg;
+  if (p.d.layout == RUA_CAT) {
+    GlobalOff f{rg.off};
+    i = owner_search(f, rg.B, j);
+    td = j - f(i);
+    base_len = f(i + 1) - f(i);
+    return true;
+  }
+  if (p.d.layout == RUA_PACK) {
+    GlobalOff f{rg.poff};
+    td = owner_search(f, rg.Tp, j);
+    i = __ldg(rg.sorted + (j - f(td)));
+    base_len = __ldg(rg.off + i + 1) - __ldg(rg.off + i);
+    return true;
+  }
+  const int64_t w = p.d.width;
+  i = j / w;
+  td = j - i * w;
+  base_len = __ldg(rg.off + i + 1) - __ldg(rg.off + i);
+  if (p.d.layout == RUA_RIGHT) td -= (w - base_len);
+  return td >= 0 && td < base_len;
+}
+
+template <typename V>
+__global__ void __launch_bounds__(kRowMapThreads)
+row_map_list_kernel(const RowMapParams p, const uint8_t* const* __restrict__ src_list, int64_t row_bytes) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = (int64_t)blockIdx.x * (kRowMapThreads / 32) + (threadIdx.x >> 5);
+  const int rpw = p.rows_per_warp;
+  const int64_t rows = p.d.rows;
+  const int64_t j0 = warp * rpw;
+  if (j0 >= rows) return;
+  // phase 1: one lane per destination row finds the ADDRESS its bytes come from (0 = padding, -1 = no row)
+  long long saddr = -1;
+  {
+    const int64_t j = j0 + lane;
+    if (lane < rpw && j < rows) {
+      int64_t i, td, len;
+      saddr = decode_dst(p, j, i, td, len) ? (long long)__ldg(reinterpret_cast<const unsigned long long*>(src_list) + i) + td * row_bytes : 0;
+    }
+  }
+  const int lpr = p.lanes_per_row;
+  const int groups = 32 / lpr;
+  const int g = lane / lpr, l = lane - g * lpr;
+  const int64_t cols_per = ceil_div(p.row_vecs, (int64_t)p.col_splits);
+  const int64_t c0 = (int64_t)blockIdx.y * cols_per;
+  const int64_t c1 = c0 + cols_per < p.row_vecs ? c0 + cols_per : p.row_vecs;
+  V* __restrict__ dst = reinterpret_cast<V*>(p.dst);
+  for (int r0 = 0; r0 < rpw; r0 += groups) {
+    const int r = r0 + g;
+    const long long sa = shfl_i64(saddr, r & 31);
+    if (r >= rpw || sa == -1) continue;
+    V* drow_p = dst + (j0 + r) * p.row_vecs;
+    if (sa != 0) {
+      const V* srow_p = reinterpret_cast<const V*>((uintptr_t)sa);
+      constexpr int U = sizeof(V) >= 32 ? kUnroll / 2 : kUnroll;
+      int64_t c = c0 + l;
+      for (; c + (int64_t)(U - 1) * lpr < c1; c += (int64_t)U * lpr) {
+        V v[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) v[u] = ld_stream(srow_p + c + (int64_t)u * lpr);
+#pragma unroll
+        for (int u = 0; u < U; ++u) st_stream(drow_p + c + (int64_t)u * lpr, v[u]);
+      }
+      for (; c < c1; c += lpr) st_stream(drow_p + c, ld_stream(srow_p + c));
+    } else {
+      for (int64_t c = c0 + l; c < c1; c += lpr) st_stream(drow_p + c, make_fill<V>(p.fill, c * (int64_t)sizeof(V)));
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 // K5 -- fused conversion + output gather (multi-GPU).  The tokens of the LOCAL shard are
 // walked in cat order; token (i, t) is read once from the local source layout (C, L, R or P) and stored
 // to row base_k[i] + t of EVERY destination k: the windows of all peer GPUs (plain stores through NVLink
@@ -769,6 +847,38 @@ static int launch_row_map(RowMapParams& p, int64_t row_bytes, int64_t rows, cuda
   return check_launch();
 }
 
+static int launch_row_map_list(RowMapParams& p, const uint8_t* const* src_list, int src_align, int64_t row_bytes,
+                               int64_t rows, cudaStream_t st) {
+  if (rows <= 0 || row_bytes <= 0) return RUA_OK;
+  uintptr_t a = (uintptr_t)p.dst | (uintptr_t)row_bytes | (uintptr_t)src_align;
+  int vec = row_bytes >= 128 ? 32 : 16;
+  while (vec > 1 && (a & (uintptr_t)(vec - 1))) vec >>= 1;
+  p.row_vecs = row_bytes / vec;
+  int lpr = 1;
+  while (lpr < 32 && lpr < p.row_vecs) lpr <<= 1;
+  p.lanes_per_row = lpr;
+  const int64_t target_warps = (int64_t)kNumSMs * 32;
+  int rpw = 32;
+  while (rpw > 32 / lpr && rpw > 1 && ceil_div(rows, rpw) < target_warps) rpw >>= 1;
+  p.rows_per_warp = rpw;
+  const int64_t warps = ceil_div(rows, rpw);
+  int splits = 1;
+  while (warps * splits < target_warps && p.row_vecs / (splits * 2) >= 32 * kUnroll && splits < 64) splits *= 2;
+  p.col_splits = splits;
+  const int64_t blocks = ceil_div(warps, kRowMapThreads / 32);
+  if (blocks >= (1ll << 31)) return RUA_ERR_UNSUPPORTED;
+  dim3 grid((unsigned)blocks, (unsigned)splits);
+  switch (vec) {
+    case 32: row_map_list_kernel<V256><<<grid, kRowMapThreads, 0, st>>>(p, src_list, row_bytes); break;
+    case 16: row_map_list_kernel<uint4><<<grid, kRowMapThreads, 0, st>>>(p, src_list, row_bytes); break;
+    case 8: row_map_list_kernel<uint2><<<grid, kRowMapThreads, 0, st>>>(p, src_list, row_bytes); break;
+    case 4: row_map_list_kernel<unsigned int><<<grid, kRowMapThreads, 0, st>>>(p, src_list, row_bytes); break;
+    case 2: row_map_list_kernel<unsigned short><<<grid, kRowMapThreads, 0, st>>>(p, src_list, row_bytes); break;
+    default: row_map_list_kernel<unsigned char><<<grid, kRowMapThreads, 0, st>>>(p, src_list, row_bytes); break;
+  }
+  return check_launch();
+}
+
 static int launch_row_map_multi(RowMapParams& p, const MultiDst& m, int64_t row_bytes, int64_t rows, cudaStream_t st) {
   if (rows <= 0 || row_bytes <= 0) return RUA_OK;
   uintptr_t a = (uintptr_t)p.src | (uintptr_t)row_bytes;
@@ -920,6 +1030,30 @@ int rua_scatter_rows_multi(const void* src, const int64_t* index, int64_t n, int
     m.base[k] = index;
   }
   return launch_row_map_multi(p, m, row_bytes, n, (cudaStream_t)stream);
+}
+
+int rua_row_map_list(const void* const* src_list, int32_t src_align, void* dst, int64_t row_bytes,
+                     const rua_ragged_t* ragged, const rua_side_t* dst_side, const void* fill_host, int32_t fill_bytes,
+                     rua_stream_t stream) {
+  if (!ragged || !valid_side(dst_side) || row_bytes < 0) return RUA_ERR_INVALID;
+  if (dst_side->rows == 0 || row_bytes == 0) return RUA_OK;
+  if (!src_list || !dst || !ragged->off || ragged->B <= 0) return RUA_ERR_INVALID;
+  if (src_align < 1 || (src_align & (src_align - 1))) return RUA_ERR_INVALID;
+  if (dst_side->len_xform != RUA_LEN_SAME) return RUA_ERR_INVALID;
+  if (dst_side->layout == RUA_PACK && (!ragged->poff || !ragged->sorted)) return RUA_ERR_INVALID;
+  if (fill_bytes != 0 && fill_bytes != 1 && fill_bytes != 2 && fill_bytes != 4 && fill_bytes != 8 && fill_bytes != 16)
+    return RUA_ERR_INVALID;
+  if (fill_bytes > 0 && (!fill_host || row_bytes % fill_bytes != 0)) return RUA_ERR_INVALID;
+  RowMapParams p{};
+  p.dst = (uint8_t*)dst;
+  p.rg = *ragged;
+  p.d = *dst_side;
+  p.s.layout = RUA_CAT;
+  uint8_t pat[16] = {0};
+  if (fill_bytes > 0)
+    for (int k = 0; k < 16; ++k) pat[k] = ((const uint8_t*)fill_host)[k % fill_bytes];
+  p.fill = make_uint4(((uint32_t*)pat)[0], ((uint32_t*)pat)[1], ((uint32_t*)pat)[2], ((uint32_t*)pat)[3]);
+  return launch_row_map_list(p, (const uint8_t* const*)src_list, src_align, row_bytes, dst_side->rows, (cudaStream_t)stream);
 }
 
 }  // extern "C"

@@ -191,6 +191,20 @@ def run_reference(args):
 # --------------------------------------------------------------------------------------------------
 # our arm
 # --------------------------------------------------------------------------------------------------
+def bind_to_gpu_numa_node(local: int):
+    """Pin this rank's host threads to the CPUs NVML reports as local to its GPU BEFORE any pinned buffer is
+    allocated (first touch then places the staging memory on the GPU's NUMA node).  Only matters for the e2e leg of
+    multi-GPU runs, where all ranks stream through host memory at once.  Best effort: returns what was done."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        handle = pynvml.nvmlDeviceGetHandleByIndex(local)
+        pynvml.nvmlDeviceSetCpuAffinity(handle)
+        return f'bound to {len(os.sched_getaffinity(0))} CPUs local to GPU {local}'
+    except Exception as e:   # no NVML / no permission: keep whatever the launcher set
+        return f'unbound ({type(e).__name__})'
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -205,6 +219,7 @@ def run_ours(args):
         raise SystemExit(f'--gpus {args.gpus} but WORLD_SIZE={world}')
     torch.cuda.set_device(local)
     dev = torch.device('cuda', local)
+    numa = bind_to_gpu_numa_node(local) if world > 1 else 'not bound (single GPU: the cpu_baseline leg uses every host core)'
     if world > 1:
         dist.init_process_group('nccl', device_id=dev)
     lib = _lib.load()
@@ -395,7 +410,7 @@ def run_ours(args):
                     'what': 'every step: pinned host C batch -> H2D -> same step through the public API -> D2H of the '
                             'round-tripped C data, segment_sum and segment_max; copy-in / compute / copy-out on three '
                             'streams so that neighbouring steps overlap (PCIe-bound: 2.1 GB each way per step)'},
-            'gpu_launches': int(launches), 'clocks': clk,
+            'gpu_launches': int(launches), 'clocks': clk, 'host_affinity': numa,
         }
         if gather is not None:
             line['output_gather'] = gather

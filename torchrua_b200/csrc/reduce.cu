@@ -33,22 +33,29 @@ int flat_launch(int32_t dtype, int64_t H, int32_t op, const void* data, const in
 // ---------------------------------------------------------------------------------------------
 // main kernel
 // ---------------------------------------------------------------------------------------------
-template <typename T, int V, int OP, bool GATHER>
+template <typename T, int V, int OP, bool GATHER, bool PACKED>
 __global__ void __launch_bounds__(kRedThreads, Store<T>::kMinBlocks)
 segreduce_kernel(const T* __restrict__ data, const int64_t* __restrict__ ridx, const int64_t* __restrict__ off,
                  int64_t N, int64_t S, int64_t H, int R, T* __restrict__ out, typename Store<T>::Acc* __restrict__ head,
-                 typename Store<T>::Acc* __restrict__ tail, int64_t* __restrict__ tail_seg, RedHeader* hdr) {
+                 typename Store<T>::Acc* __restrict__ tail, int64_t* __restrict__ tail_seg, RedHeader* hdr,
+                 int lanes_log2, int64_t chunks) {
   using A = typename Store<T>::Acc;
   constexpr bool kFast = sizeof(T) == 2;  // 16-bit storage: 1e-2 tolerance, approximate exp is plenty
   constexpr int P = OpInfo<OP>::kParts;
-  const int64_t chunk = blockIdx.x;
-  const int64_t col = ((int64_t)blockIdx.y * blockDim.x + threadIdx.x) * V;
-  const bool active = col < H;
-  const int64_t row0 = chunk * R;
+  // 2^lanes_log2 threads span one row (16 bytes each).  Rows of >= 32 vectors: that is the whole CTA (one chunk per
+  // CTA, boundaries CTA-uniform).  Shorter rows (32 .. 256 bytes): the CTA hosts blockDim / lanes chunks side by
+  // side, one per thread group, so that no lane idles; groups of a warp then diverge at their own boundaries.
+  // (a compile-time switch: the extra index arithmetic made the wide-row logsumexp instance spill at its 80 registers)
+  const int lanes = PACKED ? 1 << lanes_log2 : (int)blockDim.x;
+  const int64_t chunk = PACKED ? (int64_t)blockIdx.x * (blockDim.x >> lanes_log2) + (threadIdx.x >> lanes_log2) : (int64_t)blockIdx.x;
+  const int64_t col = PACKED ? ((int64_t)blockIdx.y * lanes + (threadIdx.x & (lanes - 1))) * V
+                             : ((int64_t)blockIdx.y * blockDim.x + threadIdx.x) * V;
+  const bool active = PACKED ? (col < H && chunk < chunks) : col < H;
+  const int64_t row0 = (!PACKED || chunk < chunks) ? chunk * R : N;
   const int64_t row1 = row0 + R < N ? row0 + R : N;
 
   GlobalOff g{off};
-  int64_t s = owner_search(g, S, row0);
+  int64_t s = owner_search(g, S, (!PACKED || row0 < N) ? row0 : (N > 0 ? N - 1 : 0));
   int64_t seg_beg = __ldg(off + s), seg_end = __ldg(off + s + 1);
   bool open = seg_beg < row0;   // the segment began in an earlier chunk
   bool pending = false;
@@ -128,7 +135,8 @@ segreduce_kernel(const T* __restrict__ data, const int64_t* __restrict__ ridx, c
   }
   if (OpInfo<OP>::kIsLse) ext = min_num(ext, packed_min_to_acc<T, V>(ext2));
   // tell the span kernel which segment (if any) starts in this chunk and runs past its end
-  if (threadIdx.x == 0 && blockIdx.y == 0) tail_seg[chunk] = (pending && !open) ? s : -1;
+  if ((PACKED ? ((threadIdx.x & (lanes - 1)) == 0 && chunk < chunks) : threadIdx.x == 0) && blockIdx.y == 0)
+    tail_seg[chunk] = (pending && !open) ? s : -1;
   if (pending && active) {
     // the segment continues in the next chunk: whole-chunk pieces go to `head`, suffix pieces to `tail`
     store_partial<A, V, OP>((open ? head : tail) + chunk * P * H, H, col, st);
@@ -237,6 +245,8 @@ struct RedPlan {
   bool flat;          // narrow rows: rows-on-lanes kernel
   int vector_loads;
   int32_t dtype;
+  int lanes_log2;     // main kernel: 2^lanes_log2 threads per row ...
+  int main_threads;   // ... in CTAs of this many threads (several chunks per CTA when rows are short)
 };
 
 static RedPlan plan_reduce(int64_t N, int64_t H, int32_t dtype, int32_t op, const void* data, const void* out) {
@@ -249,6 +259,8 @@ static RedPlan plan_reduce(int64_t N, int64_t H, int32_t dtype, int32_t op, cons
     p.vector_loads = (((uintptr_t)data) & 31u) == 0 ? 2 : ((((uintptr_t)data) & 15u) == 0 ? 1 : 0);   // 256- / 128-bit loads
     p.vec = 1;
     p.threads = 32;
+    p.lanes_log2 = 5;
+    p.main_threads = 32;
     p.col_tiles = 1;
     p.R = flat_rows_per_tile(dtype, H);
     p.chunks = N > 0 ? ceil_div(N, p.R) : 0;
@@ -263,9 +275,16 @@ static RedPlan plan_reduce(int64_t N, int64_t H, int32_t dtype, int32_t op, cons
   while (threads < kRedThreads && threads < hv) threads <<= 1;
   p.threads = threads;
   p.col_tiles = ceil_div(hv, threads);
+  // rows shorter than a warp (hv < 32 vectors): pack kRedThreads / lanes chunks into one CTA
+  int lanes = threads, lg = 0;
+  if (hv < 32 && p.vec > 1) { lanes = 1; while (lanes < hv) lanes <<= 1; }
+  while ((1 << lg) < lanes) ++lg;
+  p.lanes_log2 = lg;
+  p.main_threads = (hv < 32 && p.vec > 1) ? kRedThreads : threads;
+  const int cpc = p.main_threads / lanes;   // chunks per CTA
   // largest chunk that still gives every SM ~8 CTAs
   int R = 256;
-  while (R > 32 && ceil_div(N, R) * p.col_tiles < (int64_t)kNumSMs * 8) R >>= 1;
+  while (R > 32 && ceil_div(ceil_div(N, R), cpc) * p.col_tiles < (int64_t)kNumSMs * 8) R >>= 1;
   p.R = R;
   p.chunks = N > 0 ? ceil_div(N, R) : 0;
   p.part_elems = (size_t)p.chunks * (size_t)H * (op == RUA_LOGSUMEXP ? 2 : 1);
@@ -287,15 +306,22 @@ static int run_reduce(const RedPlan& p, const void* data, const int64_t* ridx, c
   }
   if (N > 0) {
     if (p.col_tiles > 65535) return RUA_ERR_UNSUPPORTED;
-    dim3 grid((unsigned)p.chunks, (unsigned)p.col_tiles);
+    dim3 grid((unsigned)ceil_div(p.chunks, p.main_threads >> p.lanes_log2), (unsigned)p.col_tiles);
     if (p.flat) {
       rc = flat_launch(p.dtype, H, OP, data, ridx, off, N, S, out, head, tail, tail_seg, hdr, ridx ? 0 : p.vector_loads, p.chunks, st);
       if (rc) return rc;
     } else {
-      if (ridx)
-        segreduce_kernel<T, V, OP, true><<<grid, p.threads, 0, st>>>((const T*)data, ridx, off, N, S, H, p.R, (T*)out, head, tail, tail_seg, hdr);
-      else
-        segreduce_kernel<T, V, OP, false><<<grid, p.threads, 0, st>>>((const T*)data, ridx, off, N, S, H, p.R, (T*)out, head, tail, tail_seg, hdr);
+#define RUA_LAUNCH_SEGREDUCE(G_, P_)                                                                              \
+  segreduce_kernel<T, V, OP, G_, P_><<<grid, p.main_threads, 0, st>>>((const T*)data, ridx, off, N, S, H, p.R, (T*)out, \
+                                                                      head, tail, tail_seg, hdr, p.lanes_log2, p.chunks)
+      const bool packed = (p.main_threads >> p.lanes_log2) > 1;
+      if constexpr (V > 1) {   // packing exists for the vectorised instances only (V = 1 is the odd-alignment fallback)
+        if (packed) { if (ridx) RUA_LAUNCH_SEGREDUCE(true, true); else RUA_LAUNCH_SEGREDUCE(false, true); }
+        else { if (ridx) RUA_LAUNCH_SEGREDUCE(true, false); else RUA_LAUNCH_SEGREDUCE(false, false); }
+      } else {
+        if (ridx) RUA_LAUNCH_SEGREDUCE(true, false); else RUA_LAUNCH_SEGREDUCE(false, false);
+      }
+#undef RUA_LAUNCH_SEGREDUCE
       if ((rc = check_launch())) return rc;
     }
     if (p.chunks > 1) {

@@ -51,12 +51,16 @@ struct SegCursor {
 template <typename T, int V, int OP>
 __global__ void __launch_bounds__(kRedThreads)
 tie_count_kernel(const T* __restrict__ data, const T* __restrict__ out, const int64_t* __restrict__ off, int64_t N,
-                 int64_t S, int64_t H, int R, int* __restrict__ counts) {
+                 int64_t S, int64_t H, int R, int* __restrict__ counts, int lanes_log2) {
   using A = typename Store<T>::Acc;
-  const int64_t col = ((int64_t)blockIdx.y * blockDim.x + threadIdx.x) * V;
-  const bool active = col < H;
-  const int64_t row0 = (int64_t)blockIdx.x * R;
+  // 2^lanes_log2 threads span one row; short rows: the CTA hosts several chunks side by side (see reduce.cu)
+  const int lanes = 1 << lanes_log2;
+  const int64_t chunk = (int64_t)blockIdx.x * (blockDim.x >> lanes_log2) + (threadIdx.x >> lanes_log2);
+  const int64_t col = ((int64_t)blockIdx.y * lanes + (threadIdx.x & (lanes - 1))) * V;
+  const int64_t row0 = chunk * R;
+  const bool active = col < H && row0 < N;
   const int64_t row1 = row0 + R < N ? row0 + R : N;
+  if (row0 >= N) return;
   SegCursor cur;
   cur.init(off, S, row0);
   A o[V];
@@ -91,13 +95,15 @@ template <typename T, int V, int OP>
 __global__ void __launch_bounds__(kRedThreads)
 segreduce_bwd_kernel(const T* __restrict__ gout, const T* __restrict__ out, const T* __restrict__ data,
                      const int64_t* __restrict__ off, int64_t N, int64_t S, int64_t H, int R,
-                     T* __restrict__ grad, const int* __restrict__ counts) {
+                     T* __restrict__ grad, const int* __restrict__ counts, int lanes_log2) {
   using A = typename Store<T>::Acc;
   constexpr bool kNeedsX = OP == RUA_MAX || OP == RUA_MIN || OP == RUA_PROD || OP == RUA_LOGSUMEXP;
   constexpr bool kNeedsOut = kNeedsX;
-  const int64_t col = ((int64_t)blockIdx.y * blockDim.x + threadIdx.x) * V;
-  if (col >= H) return;
-  const int64_t row0 = (int64_t)blockIdx.x * R;
+  const int lanes = 1 << lanes_log2;
+  const int64_t chunk = (int64_t)blockIdx.x * (blockDim.x >> lanes_log2) + (threadIdx.x >> lanes_log2);
+  const int64_t col = ((int64_t)blockIdx.y * lanes + (threadIdx.x & (lanes - 1))) * V;
+  const int64_t row0 = chunk * R;
+  if (col >= H || row0 >= N) return;
   const int64_t row1 = row0 + R < N ? row0 + R : N;
   SegCursor cur;
   cur.init(off, S, row0);
@@ -172,19 +178,24 @@ static int run_bwd(const void* gout, const void* out, const void* data, const in
   while (threads < kRedThreads && threads < hv) threads <<= 1;
   int64_t col_tiles = ceil_div(hv, threads);
   if (col_tiles > 65535) return RUA_ERR_UNSUPPORTED;
+  int lanes = threads;
+  if (hv < 32) { lanes = 1; while (lanes < hv) lanes <<= 1; threads = kRedThreads; }   // short rows: chunks side by side
+  int lg = 0;
+  while ((1 << lg) < lanes) ++lg;
+  const int cpc = threads / lanes;
   int R = 128;
-  while (R > 16 && ceil_div(N, R) * col_tiles < (int64_t)kNumSMs * 8) R >>= 1;
-  dim3 grid((unsigned)ceil_div(N, R), (unsigned)col_tiles);
+  while (R > 16 && ceil_div(ceil_div(N, R), cpc) * col_tiles < (int64_t)kNumSMs * 8) R >>= 1;
+  dim3 grid((unsigned)ceil_div(ceil_div(N, R), cpc), (unsigned)col_tiles);
   int rc;
   int* counts = nullptr;
   if (OP == RUA_MAX || OP == RUA_MIN) {
     counts = (int*)ws;
     if ((rc = check_cuda(cudaMemsetAsync(counts, 0, (size_t)S * H * sizeof(int), st)))) return rc;
-    tie_count_kernel<T, V, OP><<<grid, threads, 0, st>>>((const T*)data, (const T*)out, off, N, S, H, R, counts);
+    tie_count_kernel<T, V, OP><<<grid, threads, 0, st>>>((const T*)data, (const T*)out, off, N, S, H, R, counts, lg);
     if ((rc = check_launch())) return rc;
   }
   segreduce_bwd_kernel<T, V, OP><<<grid, threads, 0, st>>>((const T*)gout, (const T*)out, (const T*)data, off, N, S,
-                                                           H, R, (T*)grad, counts);
+                                                           H, R, (T*)grad, counts, lg);
   return check_launch();
 }
 

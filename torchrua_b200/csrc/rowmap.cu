@@ -60,6 +60,8 @@ __device__ __forceinline__ uint32_t fast_div(uint32_t x, uint32_t m, uint32_t s)
 }
 
 constexpr int kGenericSrc = -1;   // template tag: full generality (selects, transformed lengths, pad quirks)
+constexpr int kSrcCatRev = 16;    // C -> C with the token order reversed (C.rev on narrow rows: token ids)
+constexpr int kSrcCatRoll = 17;   // C -> C rolled by tmap_arg
 
 // "simple" maps = the 12 layout conversions: identity token map, untransformed lengths, plain fill.  With the
 // source layout known at compile time the per-element address is 2-4 instructions and no branches.
@@ -519,6 +521,16 @@ __device__ __forceinline__ void tile_body(const RowMapParams& p, OffFn f, int64_
         if (base_len < 0) base_len = __ldg(p.rg.off + i + 1) - __ldg(p.rg.off + i);
         sr = source_row(p, i, td, base_len);
         if (sr == kPadRow && p.pad_mode == RUA_PAD_ROW0) sr = 0;
+      } else if (SRC == kSrcCatRev || SRC == kSrcCatRoll) {   // same layout on both sides: segment start + mapped token
+        if (base_len < 0) base_len = __ldg(p.rg.off + i + 1) - base;
+        int64_t ts;
+        if (SRC == kSrcCatRev) {
+          ts = base_len - 1 - td;
+        } else {
+          const int64_t m = (td - p.tmap_arg) % base_len;
+          ts = m < 0 ? m + base_len : m;
+        }
+        sr = base + ts;
       } else {                                   // conversions: every destination token of C / P exists in the source
         if (SRC == RUA_RIGHT && base_len < 0) base_len = __ldg(p.rg.off + i + 1) - __ldg(p.rg.off + i);
         sr = simple_source_row<SRC>(p, i, td, base_len);
@@ -771,7 +783,10 @@ static void launch_narrow(RowMapParams& p, int64_t rows, cudaStream_t st) {
   // the 12 conversions (identity token map, untransformed lengths, plain fill) run source-specialised code
   const bool simple = !indexed && p.tmap == RUA_MAP_SHIFT && p.tmap_arg == 0 && p.pad_mode == RUA_PAD_FILL &&
                       p.s.len_xform == RUA_LEN_SAME && p.d.len_xform == RUA_LEN_SAME;
-  const int srck = simple ? p.s.layout : kGenericSrc;
+  const bool cat_select = !indexed && p.s.layout == RUA_CAT && p.d.layout == RUA_CAT && p.pad_mode == RUA_PAD_FILL &&
+                          p.s.len_xform == RUA_LEN_SAME && p.d.len_xform == RUA_LEN_SAME &&
+                          (p.tmap == RUA_MAP_REV || p.tmap == RUA_MAP_ROLL);
+  const int srck = simple ? p.s.layout : (cat_select ? (p.tmap == RUA_MAP_REV ? kSrcCatRev : kSrcCatRoll) : kGenericSrc);
   const unsigned nb = (unsigned)blocks;
   if (searched) {
     switch (srck) {
@@ -779,6 +794,8 @@ static void launch_narrow(RowMapParams& p, int64_t rows, cudaStream_t st) {
       case RUA_LEFT: row_map_tile_kernel<V, RUA_LEFT><<<nb, kTileThreads, 0, st>>>(p); break;
       case RUA_RIGHT: row_map_tile_kernel<V, RUA_RIGHT><<<nb, kTileThreads, 0, st>>>(p); break;
       case RUA_PACK: row_map_tile_kernel<V, RUA_PACK><<<nb, kTileThreads, 0, st>>>(p); break;
+      case kSrcCatRev: row_map_tile_kernel<V, kSrcCatRev><<<nb, kTileThreads, 0, st>>>(p); break;
+      case kSrcCatRoll: row_map_tile_kernel<V, kSrcCatRoll><<<nb, kTileThreads, 0, st>>>(p); break;
       default: row_map_tile_kernel<V, kGenericSrc><<<nb, kTileThreads, 0, st>>>(p); break;
     }
   } else if (!indexed) {

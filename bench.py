@@ -235,14 +235,20 @@ def run_ours(args):
     lens = lens_host.to(dev)
     cap = max(p.numel() for p in parts)
     gathered = torch.empty((world, cap + 1), dtype=torch.long, device=dev) if world > 1 else None
+    meta_windows = shard.PeerWindows(world * (cap + 1) * 8) if world > 1 and args.exchange == 'peer' else None
 
     def step(d, ln):
         _native._CACHE.clear()                      # no metadata survives from one step to the next
         work = None
         c = rua.C(data=d, token_sizes=ln)
         p = c.pack()
-        if world > 1:                               # the only collective: 8 bytes per sequence of metadata; issued
-            # while the first row-map kernel runs, so neither its host-side enqueue nor NCCL is on the critical path
+        if meta_windows is not None:
+            # the only exchange on the path: 8 bytes per sequence of metadata.  One tiny kernel stores this rank's
+            # [count, lengths] row into the (world, cap+1) table of EVERY rank through the NVLink peer windows:
+            # no collective call (an NCCL all-gather costs ~0.15 ms of host time per step here, measured), no
+            # rendezvous between ranks.  A consumer of the table fences first (drain() below, once per timed region).
+            shard.push_lengths(ln, cap, meta_windows)
+        elif world > 1 and args.exchange == 'nccl':  # portable path: the same exchange as an async NCCL all-gather
             work = shard.all_gather_lengths_fixed(ln, cap, gathered, async_op=True)
         left = p.left(0)
         right = left.right(0)
@@ -264,6 +270,12 @@ def run_ours(args):
     for _ in range(max(args.warmup, 3)):
         out = step(data, lens)
     assert torch.equal(out[0].data, data), 'round trip C->P->L->R->C is not the identity'
+    if meta_windows is not None:                    # the exchanged table holds every rank's lengths
+        meta_windows.fence()
+        table = meta_windows.view((world, cap + 1), torch.long).cpu()
+        for r in range(world):
+            k = parts[r].numel()
+            assert int(table[r, 0]) == k and torch.equal(table[r, 1:1 + k], glens[parts[r]]), 'lengths exchange'
     del out
     barrier()
     clocks.begin()
@@ -273,6 +285,8 @@ def run_ours(args):
     t0.record()
     for _ in range(args.steps):
         step(data, lens)
+    if meta_windows is not None:
+        meta_windows.fence()                        # every rank's lengths have landed everywhere: part of the timed region
     t1.record()
     barrier()
     clocks.end()
@@ -403,7 +417,7 @@ def run_ours(args):
                        'batch_per_gpu': BATCH, 'tokens_per_gpu': n_tok, 'tokens_total': total_tokens, 'hidden': HIDDEN,
                        'l2': 'inputs larger than L2: 2.17 GB per ragged layout, 4.29 GB per padded layout vs 126 MB',
                        'metadata': 'recomputed every step (cache cleared)',
-                       'parallelism': f'sequence-sharded x{world}, length-balanced (snake), lengths all-gather only'},
+                       'parallelism': f'sequence-sharded x{world}, length-balanced (snake), lengths exchange only ({args.exchange if world > 1 else "none"})'},
             'roofline': roofline, 'kernels': kernels, 'cpu_baseline': cpu,
             'e2e': {'value': e2e_value, 'unit': 'tokens/s', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h,
                     'steps': e2e_steps, 'ms_per_step': float(ems) / e2e_steps,
@@ -522,6 +536,8 @@ def main():
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--no-cpu', action='store_true', help='skip the cpu_baseline leg')
     ap.add_argument('--no-gather', action='store_true', help='skip the output-gather legs of multi-GPU runs')
+    ap.add_argument('--exchange', default='peer', choices=['peer', 'nccl', 'none'],
+                    help='per-step lengths exchange of multi-GPU runs: peer-window stores (default), NCCL all-gather, or none (diagnostic)')
     args = ap.parse_args()
     if args.impl == 'reference':
         run_reference(args)

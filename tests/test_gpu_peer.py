@@ -62,6 +62,16 @@ def _worker(rank, world, port, n_gpus, results):
                 # the same sums up to the rounding of chunk-crossing segments (fp32 accumulation either way)
                 torch.testing.assert_close(got.float(), whole.float(), rtol=1e-2 if dtype == torch.bfloat16 else 1e-5,
                                            atol=1e-3)
+        # exchange (1) as peer stores: the (world, cap + 1) table of [count, lengths...] rows
+        cap = max(p.numel() for p in parts) + 3
+        for trial in range(2):                                   # second call: cached slots, one launch
+            table = shard.push_lengths(lens[parts[rank]].to(dev), cap, windows, offset_bytes=1 << 20)
+            windows.fence()
+            host = table.cpu()
+            for r in range(world):
+                k = parts[r].numel()
+                assert int(host[r, 0]) == k and torch.equal(host[r, 1:1 + k], lens[parts[r]]), (trial, r)
+            windows.fence()
         results[rank] = True
     finally:
         if windows is not None:

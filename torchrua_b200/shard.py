@@ -202,6 +202,38 @@ class PeerWindows:
         self._own, self._opened, self.ptrs = None, [], []
 
 
+def push_lengths(local_lengths: Tensor, cap: int, windows: PeerWindows, offset_bytes: int = 0) -> Tensor:
+    """exchange (1) without a collective: row ``rank`` of the (world, cap + 1) int64 table that lives at
+    ``offset_bytes`` of EVERY rank's window becomes [count, lengths...] -- ONE tiny kernel of plain peer stores
+    (rua_scatter_rows_multi over 8-byte rows; the count slot is rewritten only when the batch size changes), no
+    staging buffer, no rendezvous.  Entries beyond ``count`` are whatever was there before.  Returns this rank's
+    table (a view of its window); call ``windows.fence()`` before reading other ranks' rows."""
+    from torchrua_b200 import _lib, _native
+    lib = _lib.load()
+    dev = windows.device
+    lens = local_lengths if local_lengths.dtype == torch.long else local_lengths.long()
+    lens = lens.contiguous()
+    n = lens.numel()
+    if n > cap:
+        raise RuntimeError(f'torchrua_b200: {n} local sequences exceed the table capacity {cap}')
+    dsts = _pointer_array([p + offset_bytes for p in windows.ptrs])
+    cache = windows.__dict__.setdefault('_push_cache', {})
+    ent = cache.get((cap, offset_bytes))
+    with torch.cuda.device(dev):
+        if ent is None or ent[0] != n:
+            base = windows.rank * (cap + 1)
+            slots = torch.arange(base + 1, base + 1 + n, dtype=torch.long, device=dev)
+            count = torch.tensor([n], dtype=torch.long, device=dev)
+            first = torch.tensor([base], dtype=torch.long, device=dev)
+            _lib.check(lib.rua_scatter_rows_multi(count.data_ptr(), first.data_ptr(), 1, 8, dsts, windows.world,
+                                                  _native._stream()), 'rua_scatter_rows_multi')
+            ent = cache[(cap, offset_bytes)] = (n, slots, count, first)
+        if n > 0:
+            _lib.check(lib.rua_scatter_rows_multi(lens.data_ptr(), ent[1].data_ptr(), n, 8, dsts, windows.world,
+                                                  _native._stream()), 'rua_scatter_rows_multi')
+    return windows.view((windows.world, cap + 1), torch.long, offset_bytes)
+
+
 def _pointer_array(values):
     import ctypes
     return (ctypes.c_void_p * len(values))(*[v if v else None for v in values])

@@ -688,18 +688,23 @@ row_map_padded_kernel(const RowMapParams p) {
   }
 }
 
-// P <-> {C, L, R} with one-vector rows (<= 16 bytes: token ids, scalars).  P is time-major, the other
-// layouts are sequence-major: moving 8-byte rows one by one leaves one side with 8 useful bytes per
-// 32-byte sector.  This is a ragged TRANSPOSE instead: a CTA owns a 32 (ranks) x 32 (time steps) tile,
-// touches P along ranks (contiguous for a fixed t) and the other layout along time (contiguous for a
-// fixed sequence), and swaps the roles through a padded shared-memory tile.  Tiles that lie entirely
+// P <-> {C, L, R} with narrow rows (< 128 bytes: token ids, scalars, small feature vectors).  P is time-major, the
+// other layouts are sequence-major: moving such rows one by one leaves one side with a fraction of each DRAM page
+// (8-byte rows: 8 useful bytes per 32-byte sector; 64-byte rows: random 64-byte reads).  This is a ragged TRANSPOSE
+// instead: a CTA owns a tile of 32 ranks x TT time steps (TT = 32 / vectors-per-row), touches P along ranks (32
+// consecutive rows of one time step are contiguous) and the other layout along time (TT consecutive tokens of one
+// sequence are contiguous), and swaps the roles through a padded shared-memory tile.  Tiles that lie entirely
 // beyond the ragged frontier (batch_sizes[t0] <= r0) exit at once.
+constexpr int kTransposeTileVecs = 32 * 33;   // >= TT * (32 * rv + 1) for every rv in 1..7
+
 template <typename V, bool kFromPack>
 __global__ void __launch_bounds__(256)
-row_map_transpose_kernel(const RowMapParams p) {
-  __shared__ V tile[32][33];
+row_map_transpose_kernel(const RowMapParams p, const int TT) {
+  __shared__ V tile[kTransposeTileVecs];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int64_t r0 = (int64_t)blockIdx.x * 32, t0 = (int64_t)blockIdx.y * 32;
+  const int rv = (int)p.row_vecs;                  // vectors per row, 1..7
+  const int stride = 32 * rv + 1;                  // shared-memory vectors per time step (+1: bank skew)
+  const int64_t r0 = (int64_t)blockIdx.x * 32, t0 = (int64_t)blockIdx.y * TT;
   const rua_side_t& sq = kFromPack ? p.d : p.s;     // the sequence-major side
   const int64_t B = p.rg.B, Tp = p.rg.Tp, W = sq.width;
   const int64_t* __restrict__ poff = p.rg.poff;
@@ -710,35 +715,43 @@ row_map_transpose_kernel(const RowMapParams p) {
   const V* __restrict__ src = reinterpret_cast<const V*>(p.src);
   V* __restrict__ dst = reinterpret_cast<V*>(p.dst);
 
-  auto pack_phase = [&](const bool load) {           // lanes run over ranks: contiguous rows of P
-    for (int tt = warp; tt < 32; tt += 8) {
+  auto pack_phase = [&](const bool load) {           // lanes run over (rank, vector): contiguous rows of P
+    for (int tt = warp; tt < TT; tt += 8) {
       const int64_t t = t0 + tt;
       if (t >= Tp) break;
       const int64_t pt = __ldg(poff + t), bst = __ldg(poff + t + 1) - pt;
-      const int64_t r = r0 + lane;
-      if (r < bst) {
-        if (load) tile[tt][lane] = ld_stream(src + pt + r);
-        else st_stream(dst + pt + r, tile[tt][lane]);
+      const int64_t live = bst - r0 < 32 ? bst - r0 : 32;          // ranks of this tile alive at time t
+      const int nvec = live > 0 ? (int)live * rv : 0;
+      const int64_t base = (pt + r0) * rv;
+      for (int k = lane; k < nvec; k += 32) {
+        if (load) tile[tt * stride + k] = ld_stream(src + base + k);
+        else st_stream(dst + base + k, tile[tt * stride + k]);
       }
     }
   };
-  auto seq_phase = [&](const bool load) {            // lanes run over time: contiguous rows of one sequence
+  // lanes run over (time, vector): TT consecutive tokens of one sequence are contiguous
+  const int tt_l = rv == 1 ? lane : (int)fast_div((uint32_t)lane, p.div_rv_m, p.div_rv_s);
+  const int c_l = lane - tt_l * rv;
+  const bool lane_on = tt_l < TT;
+  auto seq_phase = [&](const bool load) {
     for (int rr = warp; rr < 32; rr += 8) {
       const int64_t r = r0 + rr;
       if (r >= B) break;
       const int64_t i = __ldg(p.rg.sorted + r);
       const int64_t o = __ldg(off + i), len = __ldg(off + i + 1) - o;
-      const int64_t t = t0 + lane;
+      const int64_t t = t0 + tt_l;
+      if (!lane_on) continue;
       int64_t row;
       if (sq.layout == RUA_CAT) row = o + t;
       else if (sq.layout == RUA_LEFT) row = i * W + t;
       else row = i * W + (W - len) + t;
+      V* cell = tile + tt_l * stride + rr * rv + c_l;
       if (load) {
-        if (t < len) tile[lane][rr] = ld_stream(src + row);
+        if (t < len) *cell = ld_stream(src + row * rv + c_l);
       } else if (t < len) {
-        st_stream(dst + row, tile[lane][rr]);
+        st_stream(dst + row * rv + c_l, *cell);
       } else if (padded_dst && t < W) {              // left-aligned padding (R destinations do not come here)
-        st_stream(dst + i * W + t, make_fill<V>(p.fill, 0));
+        st_stream(dst + (i * W + t) * rv + c_l, make_fill<V>(p.fill, (int64_t)c_l * (int64_t)sizeof(V)));
       }
     }
   };
@@ -753,9 +766,9 @@ row_map_transpose_kernel(const RowMapParams p) {
   }
 }
 
-// can the ragged transpose serve this call?  (identity token map, untransformed lengths, one vector per row)
-static bool transpose_applies(const RowMapParams& p, int64_t* grid_y) {
-  if (p.gather_index || p.scatter_index || p.row_vecs != 1) return false;
+// can the ragged transpose serve this call?  (identity token map, untransformed lengths, narrow rows)
+static bool transpose_applies(const RowMapParams& p, int64_t* grid_y, int* tt) {
+  if (p.gather_index || p.scatter_index || p.row_vecs < 1 || p.row_vecs > 7) return false;
   if (p.tmap != RUA_MAP_SHIFT || p.tmap_arg != 0 || p.pad_mode != RUA_PAD_FILL) return false;
   if (p.s.len_xform != RUA_LEN_SAME || p.d.len_xform != RUA_LEN_SAME) return false;
   const bool from_pack = p.s.layout == RUA_PACK && p.d.layout != RUA_PACK;
@@ -764,17 +777,21 @@ static bool transpose_applies(const RowMapParams& p, int64_t* grid_y) {
   if (from_pack && p.d.layout == RUA_RIGHT) return false;   // right-aligned padding is not tile-aligned
   int64_t t_extent = p.rg.Tp;
   if (from_pack && p.d.layout == RUA_LEFT && p.d.width > t_extent) t_extent = p.d.width;
-  *grid_y = ceil_div(t_extent, 32);
+  *tt = 32 / (int)p.row_vecs;
+  *grid_y = ceil_div(t_extent, *tt);
   return *grid_y >= 1 && *grid_y <= 65535 && ceil_div(p.rg.B, 32) < (1ll << 31);
 }
 
 template <typename V>
 static void launch_narrow(RowMapParams& p, int64_t rows, cudaStream_t st) {
   int64_t gy = 0;
-  if (transpose_applies(p, &gy)) {
+  int tt = 32;
+  if (transpose_applies(p, &gy, &tt)) {
+    const FastDiv dv = FastDiv::make((uint64_t)p.row_vecs);
+    p.div_rv_m = dv.m; p.div_rv_s = dv.s;
     dim3 grid((unsigned)ceil_div(p.rg.B, 32), (unsigned)gy);
-    if (p.s.layout == RUA_PACK) row_map_transpose_kernel<V, true><<<grid, 256, 0, st>>>(p);
-    else row_map_transpose_kernel<V, false><<<grid, 256, 0, st>>>(p);
+    if (p.s.layout == RUA_PACK) row_map_transpose_kernel<V, true><<<grid, 256, 0, st>>>(p, tt);
+    else row_map_transpose_kernel<V, false><<<grid, 256, 0, st>>>(p, tt);
     return;
   }
   const int64_t blocks = ceil_div(rows * p.row_vecs, kTileVecs);

@@ -697,12 +697,13 @@ row_map_padded_kernel(const RowMapParams p) {
 // beyond the ragged frontier (batch_sizes[t0] <= r0) exit at once.
 constexpr int kTransposeTileVecs = 32 * 33;   // >= TT * (32 * rv + 1) for every rv in 1..7
 
-template <typename V, bool kFromPack>
+template <typename V, bool kFromPack, int RV>       // RV = 1: one-vector rows at compile time; RV = 0: read it from p
 __global__ void __launch_bounds__(256)
-row_map_transpose_kernel(const RowMapParams p, const int TT) {
+row_map_transpose_kernel(const RowMapParams p, const int TT_) {
   __shared__ V tile[kTransposeTileVecs];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int rv = (int)p.row_vecs;                  // vectors per row, 1..7
+  const int rv = RV ? RV : (int)p.row_vecs;        // vectors per row, 1..7
+  const int TT = RV == 1 ? 32 : TT_;
   const int stride = 32 * rv + 1;                  // shared-memory vectors per time step (+1: bank skew)
   const int64_t r0 = (int64_t)blockIdx.x * 32, t0 = (int64_t)blockIdx.y * TT;
   const rua_side_t& sq = kFromPack ? p.d : p.s;     // the sequence-major side
@@ -715,17 +716,44 @@ row_map_transpose_kernel(const RowMapParams p, const int TT) {
   const V* __restrict__ src = reinterpret_cast<const V*>(p.src);
   V* __restrict__ dst = reinterpret_cast<V*>(p.dst);
 
+  // Both phases are chains of dependent loads (poff[t] -> rows; sorted[r] -> off[i] -> rows).  A warp owns 4 time
+  // steps / 4 ranks of the tile; lanes 0..3 fetch the metadata of all four AT ONCE and broadcast it, so the chain is
+  // paid once per warp instead of once per row (this kernel is latency-bound: 94 % warps active, 36 % DRAM).
   auto pack_phase = [&](const bool load) {           // lanes run over (rank, vector): contiguous rows of P
-    for (int tt = warp; tt < TT; tt += 8) {
-      const int64_t t = t0 + tt;
-      if (t >= Tp) break;
-      const int64_t pt = __ldg(poff + t), bst = __ldg(poff + t + 1) - pt;
-      const int64_t live = bst - r0 < 32 ? bst - r0 : 32;          // ranks of this tile alive at time t
-      const int nvec = live > 0 ? (int)live * rv : 0;
-      const int64_t base = (pt + r0) * rv;
-      for (int k = lane; k < nvec; k += 32) {
-        if (load) tile[tt * stride + k] = ld_stream(src + base + k);
-        else st_stream(dst + base + k, tile[tt * stride + k]);
+    int64_t my_pt = 0, my_bst = 0;
+    {
+      const int64_t t = t0 + warp + 8 * lane;
+      if (lane < 4 && warp + 8 * lane < TT && t < Tp) { my_pt = __ldg(poff + t); my_bst = __ldg(poff + t + 1) - my_pt; }
+    }
+    if constexpr (RV == 1) {   // one vector per rank: a single round, all four time steps' loads in flight together
+      V val[4];
+      bool on[4];
+      int64_t at[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int64_t pt = shfl_i64(my_pt, k), bst = shfl_i64(my_bst, k);
+        on[k] = t0 + warp + 8 * k < Tp && r0 + lane < bst;
+        at[k] = pt + r0 + lane;
+        if (load && on[k]) val[k] = ld_stream(src + at[k]);
+      }
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        if (!on[k]) continue;
+        if (load) tile[(warp + 8 * k) * stride + lane] = val[k];
+        else st_stream(dst + at[k], tile[(warp + 8 * k) * stride + lane]);
+      }
+    } else {
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int tt = warp + 8 * k;
+        const int64_t pt = shfl_i64(my_pt, k), bst = shfl_i64(my_bst, k);
+        const int64_t live = bst - r0 < 32 ? bst - r0 : 32;          // ranks of this tile alive at time t
+        const int nvec = (tt < TT && t0 + tt < Tp && live > 0) ? (int)live * rv : 0;
+        const int64_t base = (pt + r0) * rv;
+        for (int q = lane; q < nvec; q += 32) {
+          if (load) tile[tt * stride + q] = ld_stream(src + base + q);
+          else st_stream(dst + base + q, tile[tt * stride + q]);
+        }
       }
     }
   };
@@ -734,20 +762,39 @@ row_map_transpose_kernel(const RowMapParams p, const int TT) {
   const int c_l = lane - tt_l * rv;
   const bool lane_on = tt_l < TT;
   auto seq_phase = [&](const bool load) {
-    for (int rr = warp; rr < 32; rr += 8) {
-      const int64_t r = r0 + rr;
-      if (r >= B) break;
-      const int64_t i = __ldg(p.rg.sorted + r);
-      const int64_t o = __ldg(off + i), len = __ldg(off + i + 1) - o;
-      const int64_t t = t0 + tt_l;
+    int64_t my_i = 0, my_o = 0, my_len = 0;
+    {
+      const int64_t r = r0 + warp + 8 * lane;
+      if (lane < 4 && r < B) {
+        my_i = __ldg(p.rg.sorted + r);
+        my_o = __ldg(off + my_i);
+        my_len = __ldg(off + my_i + 1) - my_o;
+      }
+    }
+    const int64_t t = t0 + tt_l;
+    V val[RV == 1 ? 4 : 1];
+    if constexpr (RV == 1) {   // narrow vectors: the four ranks' row loads go out together (registers are cheap here)
+      if (load) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const int64_t i = shfl_i64(my_i, k), o = shfl_i64(my_o, k), len = shfl_i64(my_len, k);
+          const int64_t row = sq.layout == RUA_CAT ? o + t : (sq.layout == RUA_LEFT ? i * W + t : i * W + (W - len) + t);
+          if (r0 + warp + 8 * k < B && t < len) val[k] = ld_stream(src + row);
+        }
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {                      // the metadata chain was paid once; one round trip per rank here
+      const int64_t i = shfl_i64(my_i, k), o = shfl_i64(my_o, k), len = shfl_i64(my_len, k);
+      if (r0 + warp + 8 * k >= B) break;               // warp-uniform
       if (!lane_on) continue;
       int64_t row;
       if (sq.layout == RUA_CAT) row = o + t;
       else if (sq.layout == RUA_LEFT) row = i * W + t;
       else row = i * W + (W - len) + t;
-      V* cell = tile + tt_l * stride + rr * rv + c_l;
+      V* cell = tile + tt_l * stride + (warp + 8 * k) * rv + c_l;
       if (load) {
-        if (t < len) *cell = ld_stream(src + row * rv + c_l);
+        if (t < len) *cell = RV == 1 ? val[k] : ld_stream(src + row * rv + c_l);
       } else if (t < len) {
         st_stream(dst + row * rv + c_l, *cell);
       } else if (padded_dst && t < W) {              // left-aligned padding (R destinations do not come here)
@@ -790,8 +837,14 @@ static void launch_narrow(RowMapParams& p, int64_t rows, cudaStream_t st) {
     const FastDiv dv = FastDiv::make((uint64_t)p.row_vecs);
     p.div_rv_m = dv.m; p.div_rv_s = dv.s;
     dim3 grid((unsigned)ceil_div(p.rg.B, 32), (unsigned)gy);
-    if (p.s.layout == RUA_PACK) row_map_transpose_kernel<V, true><<<grid, 256, 0, st>>>(p, tt);
-    else row_map_transpose_kernel<V, false><<<grid, 256, 0, st>>>(p, tt);
+    const bool from_pack = p.s.layout == RUA_PACK;
+    if (p.row_vecs == 1) {
+      if (from_pack) row_map_transpose_kernel<V, true, 1><<<grid, 256, 0, st>>>(p, tt);
+      else row_map_transpose_kernel<V, false, 1><<<grid, 256, 0, st>>>(p, tt);
+    } else {
+      if (from_pack) row_map_transpose_kernel<V, true, 0><<<grid, 256, 0, st>>>(p, tt);
+      else row_map_transpose_kernel<V, false, 0><<<grid, 256, 0, st>>>(p, tt);
+    }
     return;
   }
   const int64_t blocks = ceil_div(rows * p.row_vecs, kTileVecs);

@@ -466,24 +466,33 @@ def row_map(src_flat: Tensor, spec: MapSpec, fill_value=0) -> Tensor:
 HOST_SORT_MAX_B = 1 << 16      # above this the stable sort for P.new runs on the device (K0) instead of numpy
 
 
+def host_metadata(lengths, with_pack: bool):
+    """Pure host side of the constructors: (B, N, T, [len, off(B+1)] + ([sorted, unsorted, batch_sizes, poff(T+1)] if
+    with_pack), batch_sizes) as int64 numpy arrays -- the same closed forms the K0 kernels compute on the device
+    (stable descending order: ties by ascending index).  No torch, no CUDA: covered by the CPU test-suite."""
+    import numpy as np
+    lens_np = np.asarray(lengths, dtype=np.int64).reshape(-1)
+    b = int(lens_np.size)
+    n = int(lens_np.sum()) if b else 0
+    t = int(lens_np.max()) if b else 0
+    parts = [lens_np, np.concatenate(([0], np.cumsum(lens_np))).astype(np.int64)]
+    bs = None
+    if with_pack:
+        srt = np.argsort(-lens_np, kind='stable').astype(np.int64)
+        uns = np.empty_like(srt)
+        uns[srt] = np.arange(b, dtype=np.int64)
+        bs = (np.bincount(lens_np, minlength=t + 1)[::-1].cumsum()[::-1][1:] if t > 0 else np.zeros(0, np.int64)).astype(np.int64)
+        parts += [srt, uns, bs, np.concatenate(([0], np.cumsum(bs))).astype(np.int64)]
+    return b, n, t, parts, bs
+
+
 def ragged_from_host_lengths(lengths, device: torch.device, want_pack: bool, extra_host: Optional[Tensor] = None):
     """Ragged for lengths known on the host (list construction).  Everything -- offsets, N, T and, for small
     batches, the stable descending order, batch_sizes and their prefix sums -- is computed with numpy and
     shipped in ONE pinned H2D copy; nothing is read back.  ``extra_host`` (int64) rides along in the same copy
     (the pointer table of the list kernel) and is returned as a device view."""
-    import numpy as np
-    lens_np = np.asarray(lengths, dtype=np.int64)
-    b = int(lens_np.size)
-    n = int(lens_np.sum()) if b else 0
-    t = int(lens_np.max()) if b else 0
-    host_pack = want_pack and 0 < b <= HOST_SORT_MAX_B
-    parts = [lens_np, np.concatenate(([0], np.cumsum(lens_np)))]
-    if host_pack:
-        srt = np.argsort(-lens_np, kind='stable')
-        uns = np.empty_like(srt)
-        uns[srt] = np.arange(b, dtype=np.int64)
-        bs = (np.bincount(lens_np, minlength=t + 1)[::-1].cumsum()[::-1][1:] if t > 0 else np.zeros(0, np.int64)).astype(np.int64)
-        parts += [srt.astype(np.int64), uns, bs, np.concatenate(([0], np.cumsum(bs)))]
+    b, n, t, parts, bs = host_metadata(lengths, want_pack and 0 < len(lengths) <= HOST_SORT_MAX_B)
+    host_pack = len(parts) > 2
     n_extra = 0 if extra_host is None else extra_host.numel()
     sizes = [p.size for p in parts]
     host = torch.empty(sum(sizes) + n_extra, dtype=torch.long, pin_memory=True)

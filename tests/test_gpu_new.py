@@ -108,3 +108,24 @@ def test_new_large_batch_device_sort_path(monkeypatch):
     ref = pack_sequence(tensors, enforce_sorted=False)
     assert torch.equal(pk.batch_sizes, ref.batch_sizes)
     assert torch.equal(pk.cat().data, torch.cat(tensors))
+
+
+@pytest.mark.parametrize('lengths', [[5000, 3, 10], [4097], [4096, 4096, 1], [1, 2, 3]])
+def test_pack_speculative_launch_and_its_fallback(lengths):
+    """C.pack() enqueues the conversion before batch_sizes reaches the host, assuming T <= 4096 time steps; longer
+    sequences invalidate the speculation and the conversion is redone with exact metadata."""
+    from torchrua_b200 import _native
+    _native._CACHE.clear()
+    g = torch.Generator().manual_seed(3)
+    tensors = [torch.randn((n, 6), generator=g).cuda().requires_grad_(True) for n in lengths]
+    c = C(data=torch.cat(tensors), token_sizes=torch.tensor(lengths, device='cuda'))
+    pk = c.pack()
+    ref = pack_sequence(tensors, enforce_sorted=False)
+    assert torch.equal(pk.batch_sizes, ref.batch_sizes)
+    assert torch.equal(pk.cat().data, torch.cat(tensors))
+    assert torch.equal(pk.data, ref.data) or len(set(lengths)) < len(lengths)     # identical unless ties reorder
+    w = torch.randn_like(pk.data)
+    (pk.data * w).sum().backward()
+    got = torch.cat([t.grad for t in tensors])
+    wc = P(data=w, batch_sizes=pk.batch_sizes, sorted_indices=pk.sorted_indices, unsorted_indices=pk.unsorted_indices).cat().data
+    assert torch.equal(got, wc)

@@ -74,6 +74,17 @@ def fetch(dev_tensor: Tensor) -> Tensor:
     return host
 
 
+def fetch_async(dev_tensor: Tensor):
+    """enqueue the device -> host read and return (pinned host tensor, event); ``event.synchronize()`` waits for
+    the copy only, not for kernels enqueued after it."""
+    host = torch.empty(dev_tensor.shape, dtype=dev_tensor.dtype, pin_memory=True)
+    with _on(dev_tensor.device):
+        host.copy_(dev_tensor, non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record()
+    return host, ev
+
+
 def upload(host_tensor: Tensor, device: torch.device) -> Tensor:
     """small host -> device write through pinned memory (asynchronous, stream-ordered)."""
     pinned = torch.empty(host_tensor.shape, dtype=host_tensor.dtype, pin_memory=True)
@@ -171,6 +182,7 @@ class Ragged:
     bs_cpu: Optional[Tensor] = None
     Tp: int = 0
     _keep: list = field(default_factory=list)
+    _spec_ok: bool = False            # the speculative early launch of _ensure_pack_fused held
 
     def _sync_stats(self):
         # the one inherent D2H: output shapes depend on device data (16 bytes, pinned, stream-ordered)
@@ -221,12 +233,19 @@ class Ragged:
         _cache_put(self.unsorted, 'pack', self)
         return self
 
-    def _ensure_pack_fused(self) -> 'Ragged':
-        """B <= 16384: ONE kernel (scan + bitonic sort + batch_sizes + their prefix sums) and ONE
-        device->host copy of [N, T, batch_sizes]."""
+    def _ensure_pack_fused(self, early=None) -> 'Ragged':
+        """B <= 8192: ONE kernel (scan + radix sort + batch_sizes + their prefix sums) and ONE device->host copy of
+        [N, T, batch_sizes].
+
+        ``early(self)`` (optional) is called after the kernel and the copy are ENQUEUED but before the host waits for
+        them, with the pack side in a speculative state (Tp = cap time steps, poff padded with N): a consumer that
+        does not need N, T or batch_sizes on the host -- the C -> P row map, whose row count is the data's --
+        launches there, and the host round trip overlaps it instead of idling the GPU.  ``self._spec_ok`` tells the
+        caller whether the speculation held (T <= cap)."""
         lib = _lib.load()
         dev = self.device
         cap = self._T if self._T is not None else FUSED_CAP
+        self._spec_ok = False
         while True:
             with _on(dev):
                 self.sorted = torch.empty(self.B, dtype=torch.long, device=dev)
@@ -236,9 +255,16 @@ class Ragged:
                 _lib.check(lib.rua_meta_fused(self.len.data_ptr(), self.B, self.off.data_ptr(), self.sorted.data_ptr(),
                                               self.unsorted.data_ptr(), hostbuf.data_ptr(), poff.data_ptr(), cap,
                                               _stream()), 'rua_meta_fused')
-            host = fetch(hostbuf)
+            host, ev = fetch_async(hostbuf)
+            speculated = False
+            if early is not None:
+                self.poff, self.Tp = poff, cap
+                early(self)
+                early, speculated = None, True      # at most once
+            ev.synchronize()
             n, t = int(host[0]), int(host[1])
             if t <= cap:
+                self._spec_ok = speculated
                 break
             cap = t   # a sequence longer than the speculative cap: one more round trip, exact this time
         self._N, self._T, self.Tp = n, t, t
@@ -274,7 +300,7 @@ def _cache_put(key_tensor: Tensor, tag: str, value):
 FUSED_MAX_B = 8192   # == rua_meta_fused_max_batch()
 
 
-def ragged_from_lengths(token_sizes: Tensor, want_pack: bool = False) -> Ragged:
+def ragged_from_lengths(token_sizes: Tensor, want_pack: bool = False, early=None) -> Ragged:
     """lengths -> Ragged, cached per lengths tensor object + version.  One scan kernel; or, when the
     pack side is wanted and the batch is small enough, one fused kernel that produces everything."""
     hit = _cache_get(token_sizes, 'len')
@@ -285,7 +311,7 @@ def ragged_from_lengths(token_sizes: Tensor, want_pack: bool = False) -> Ragged:
     b = lens.numel()
     if want_pack and 0 < b <= FUSED_MAX_B:
         rg = Ragged(device=dev, B=b, len=lens, off=torch.empty(b + 1, dtype=torch.long, device=dev))
-        rg._ensure_pack_fused()
+        rg._ensure_pack_fused(early)
     else:
         off, stats = scan(lens)
         rg = Ragged(device=dev, B=b, len=lens, off=off, stats=stats)

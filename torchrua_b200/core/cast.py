@@ -68,11 +68,24 @@ R.left = to_left
 def to_pack(self: Z, sorted_indices: Optional[Tensor] = None) -> P:
     """``sorted_indices`` (extension): pack with an externally supplied permutation instead of the
     device sort -- parity mode against the reference's non-stable CPU sort (SURVEY.md 8c hazard 1)."""
+    data = None
     if sorted_indices is None:
-        rg = self._ragged(want_pack=True)   # small batches: one fused metadata kernel, one D2H
+        early_out, early, n_rows = [], None, -1
+        if isinstance(self, C):
+            # The row count of the result is the data's, so the conversion does not need N, T or batch_sizes on the
+            # host: it is enqueued right behind the fused metadata kernel, and the device->host round trip that
+            # PackedSequence's host-side batch_sizes requires overlaps it instead of idling the GPU.
+            n_rows = self.data.size()[0]
+
+            def early(rg):
+                early_out.append(_convert(self, rg, SideSpec(PACK, rows=n_rows)))
+        rg = self._ragged(want_pack=True, early=early)   # small batches: one fused metadata kernel, one D2H
+        if early_out and rg._spec_ok and rg.N == n_rows:
+            data = early_out[0]
     else:
         rg = _native.with_injected_pack(self._ragged(), sorted_indices)
-    data = _convert(self, rg, SideSpec(PACK, rows=rg.N))
+    if data is None:
+        data = _convert(self, rg, SideSpec(PACK, rows=rg.N))
     return P(data=data, batch_sizes=rg.bs_cpu, sorted_indices=rg.sorted, unsorted_indices=rg.unsorted)
 
 

@@ -206,6 +206,10 @@ meta_fused_kernel(const int64_t* __restrict__ len, int B, int Bpad, int64_t* __r
     }
   }
   if (tid == 0) poff[Tc] = Tc == T ? total : -1;  // exact only when nothing was cut off by cap
+  // entries beyond T are N as well, so that a consumer launched BEFORE the host has read T (speculative C -> P
+  // conversion) can search poff[0 .. cap] as if there were cap time steps: the extra ones are empty
+  if (Tc == T)
+    for (int t = Tc + 1 + tid; t <= cap; t += kFusedThreads) poff[t] = total;
 }
 
 }  // namespace rua

@@ -30,9 +30,9 @@ class TokenSizesOps:
     def detach(self):
         return type(self)(data=self.data.detach(), token_sizes=self.token_sizes.detach())
 
-    def _ragged(self, want_pack: bool = False) -> '_native.Ragged':
+    def _ragged(self, want_pack: bool = False, early=None) -> '_native.Ragged':
         _native.require_cuda(self.data, self.token_sizes)
-        return _native.ragged_from_lengths(self.token_sizes, want_pack)
+        return _native.ragged_from_lengths(self.token_sizes, want_pack, early)
 
 
 def _make_cast(dtype):

@@ -198,7 +198,12 @@ def bind_to_gpu_numa_node(local: int):
     try:
         import pynvml
         pynvml.nvmlInit()
-        handle = pynvml.nvmlDeviceGetHandleByIndex(local)
+        try:   # NVML does not honour CUDA_VISIBLE_DEVICES: address the device by its PCI id
+            import torch
+            pr = torch.cuda.get_device_properties(local)
+            handle = pynvml.nvmlDeviceGetHandleByPciBusId(f'{pr.pci_domain_id:08x}:{pr.pci_bus_id:02x}:{pr.pci_device_id:02x}.0')
+        except Exception:
+            handle = pynvml.nvmlDeviceGetHandleByIndex(local)
         pynvml.nvmlDeviceSetCpuAffinity(handle)
         return f'bound to {len(os.sched_getaffinity(0))} CPUs local to GPU {local}'
     except Exception as e:   # no NVML / no permission: keep whatever the launcher set

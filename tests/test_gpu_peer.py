@@ -4,6 +4,7 @@ against (a) the plain single-process result and (b) the NCCL/gloo all_gather + p
 Two processes.  With >= 2 GPUs each rank owns one (NCCL, stores cross NVLink); on a one-GPU box both ranks share
 cuda:0 (gloo control plane, CUDA IPC mappings of the same device) so the kernels, the window plumbing and the
 fence protocol are still exercised end to end."""
+import datetime
 import os
 import socket
 
@@ -27,9 +28,9 @@ def _worker(rank, world, port, n_gpus, results):
     dev = torch.device('cuda', rank % n_gpus)
     torch.cuda.set_device(dev)
     if n_gpus >= world:
-        dist.init_process_group('nccl', rank=rank, world_size=world, device_id=dev)
+        dist.init_process_group('nccl', rank=rank, world_size=world, device_id=dev, timeout=datetime.timedelta(seconds=180))
     else:
-        dist.init_process_group('gloo', rank=rank, world_size=world)
+        dist.init_process_group('gloo', rank=rank, world_size=world, timeout=datetime.timedelta(seconds=180))
     import torchrua_b200 as rua
     from torchrua_b200 import shard
     windows = None
@@ -79,6 +80,7 @@ def _worker(rank, world, port, n_gpus, results):
         dist.destroy_process_group()
 
 
+@pytest.mark.timeout(600)
 def test_fused_gather_two_ranks():
     world = 2
     n_gpus = torch.cuda.device_count()

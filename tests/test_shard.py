@@ -84,6 +84,7 @@ def _worker(rank, world, port, results):
         dist.destroy_process_group()
 
 
+@pytest.mark.timeout(600)
 def test_exchanges_gloo_world2():
     world = 2
     port = free_port()

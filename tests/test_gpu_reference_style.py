@@ -17,7 +17,11 @@ import torchrua  # noqa: E402
 from torchrua import C, L, P, R, Z  # noqa: E402
 
 KINDS = Z.__args__
-COMMON = dict(deadline=None, max_examples=12, derandomize=True)
+import os  # noqa: E402
+
+# RUA_HYPOTHESIS_EXAMPLES=200 turns this file into a fuzzing session (the default keeps the suite under a minute)
+EXAMPLES = int(os.environ.get('RUA_HYPOTHESIS_EXAMPLES', '12'))
+COMMON = dict(deadline=None, max_examples=EXAMPLES, derandomize=EXAMPLES <= 12)
 
 
 def expected_new(kind, tensors, padding_value=0):
@@ -152,7 +156,7 @@ def test_seg(name, token_sizes, dim, seq_kind, dur_kind):
     assert_grad_close(actual=actual.data, expected=expected.data, inputs=inputs)
 
 
-@settings(deadline=None, max_examples=6, derandomize=True)
+@settings(deadline=None, max_examples=max(6, EXAMPLES // 4), derandomize=EXAMPLES <= 12)
 @given(token_sizes_batch=sizes(TINY_BATCH_SIZE, TINY_BATCH_SIZE, TINY_TOKEN_SIZE), dim=sizes(FEATURE_DIM),
        hidden=sizes(FEATURE_DIM), kind=st.sampled_from(KINDS))
 def test_compose_feeds_an_lstm(token_sizes_batch, dim, hidden, kind):

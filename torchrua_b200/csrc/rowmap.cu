@@ -688,6 +688,87 @@ row_map_padded_kernel(const RowMapParams p) {
   }
 }
 
+// C -> L / R with ONE-VECTOR rows (token ids, per-token scalars: the padded batch every model builds).  The general
+// kernel above decodes every 8-byte element on its own (fast division, two shared-memory reads, validity test) and is
+// issue-bound at 72 % issue-active.  Here a thread owns FOUR consecutive destination vectors: one division, one pair of
+// shared-memory reads (two when the group straddles a row end), four loads, ONE wide store.
+template <typename V> __device__ __forceinline__ void store4(V* p, const V& a, const V& b, const V& c, const V& d) {
+  st_stream(p, a); st_stream(p + 1, b); st_stream(p + 2, c); st_stream(p + 3, d);
+}
+template <> __device__ __forceinline__ void store4<uint2>(uint2* p, const uint2& a, const uint2& b, const uint2& c, const uint2& d) {
+  auto u64 = [](const uint2& v) { return ((unsigned long long)v.y << 32) | v.x; };
+  st_stream(reinterpret_cast<V256*>(p), V256{u64(a), u64(b), u64(c), u64(d)});
+}
+template <> __device__ __forceinline__ void store4<unsigned int>(unsigned int* p, const unsigned int& a, const unsigned int& b,
+                                                                 const unsigned int& c, const unsigned int& d) {
+  st_stream(reinterpret_cast<uint4*>(p), make_uint4(a, b, c, d));
+}
+template <> __device__ __forceinline__ void store4<uint4>(uint4* p, const uint4& a, const uint4& b, const uint4& c, const uint4& d) {
+  auto u64 = [](unsigned lo, unsigned hi) { return ((unsigned long long)hi << 32) | lo; };
+  st_stream(reinterpret_cast<V256*>(p), V256{u64(a.x, a.y), u64(a.z, a.w), u64(b.x, b.y), u64(b.z, b.w)});
+  st_stream(reinterpret_cast<V256*>(p) + 1, V256{u64(c.x, c.y), u64(c.z, c.w), u64(d.x, d.y), u64(d.z, d.w)});
+}
+
+template <typename V>
+__global__ void __launch_bounds__(kTileThreads)
+row_map_padded_cat1_kernel(const RowMapParams p) {
+  __shared__ int s_rel[kTileCap];            // off[i0 + k] - off[i0]
+  const int tid = threadIdx.x;
+  const int64_t total = p.d.rows;             // one vector per row
+  const int64_t e0 = (int64_t)blockIdx.x * kTileVecs;
+  const int n_e = (int)(e0 + kTileVecs < total ? kTileVecs : total - e0);
+  const uint32_t W = (uint32_t)p.d.width;     // 4 <= W <= 2^30 (checked by the launcher)
+  const int64_t i0 = e0 / W;
+  const int64_t i1 = (e0 + n_e - 1) / W;
+  const uint32_t head = (uint32_t)(e0 - i0 * W);
+  const int cnt = (int)(i1 - i0 + 2);
+  const int64_t base0 = __ldg(p.rg.off + i0);
+  for (int k = tid; k < cnt; k += kTileThreads) {
+    const int64_t d = __ldg(p.rg.off + i0 + k) - base0;
+    s_rel[k] = d > (1 << 30) ? (1 << 30) : (int)d;
+  }
+  __syncthreads();
+  const bool right_dst = p.d.layout == RUA_RIGHT;
+  const V* __restrict__ src = reinterpret_cast<const V*>(p.src) + base0;
+  V* __restrict__ dst = reinterpret_cast<V*>(p.dst) + e0;
+  const V fill = make_fill<V>(p.fill, 0);
+#pragma unroll
+  for (int g = 0; g < kTileItems / 4; ++g) {
+    const int eb = (g * kTileThreads + tid) * 4;          // tile-relative, 4 consecutive destination vectors
+    if (eb >= n_e) break;
+    const uint32_t x = head + (uint32_t)eb;               // < 2^31
+    const uint32_t q = fast_div(x, p.div_wrv_m, p.div_wrv_s);
+    const uint32_t rem = x - q * W;
+    int sq = s_rel[q], len = s_rel[q + 1] - sq;
+    int shift = right_dst ? (int)W - len : 0;
+    V v[4];
+    int from[4];                                          // source vector relative to base0, or -1 = padding
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      int t = (int)rem + j;
+      if (t >= (int)W && eb + j < n_e) {                  // the group straddles a row end (at most once: W >= 4)
+        t -= (int)W;
+        if (t == 0) {
+          sq = s_rel[q + 1];
+          len = s_rel[q + 2] - sq;
+          shift = right_dst ? (int)W - len : 0;
+        }
+      }
+      const int td = t - shift;
+      from[j] = (td >= 0 && td < len && eb + j < n_e) ? sq + td : -1;
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) v[j] = from[j] >= 0 ? ld_stream(src + from[j]) : fill;
+    if (eb + 4 <= n_e) {
+      store4<V>(dst + eb, v[0], v[1], v[2], v[3]);
+    } else {
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        if (eb + j < n_e) st_stream(dst + eb + j, v[j]);
+    }
+  }
+}
+
 // P <-> {C, L, R} with narrow rows (< 128 bytes: token ids, scalars, small feature vectors).  P is time-major, the
 // other layouts are sequence-major: moving such rows one by one leaves one side with a fraction of each DRAM page
 // (8-byte rows: 8 useful bytes per 32-byte sector; 64-byte rows: random 64-byte reads).  This is a ragged TRANSPOSE
@@ -872,6 +953,12 @@ static void launch_narrow(RowMapParams& p, int64_t rows, cudaStream_t st) {
     const int64_t wrv = p.d.width * p.row_vecs;
     const FastDiv a = FastDiv::make((uint64_t)(wrv > (1ll << 30) ? 1 : wrv)), b = FastDiv::make((uint64_t)p.row_vecs);
     p.div_wrv_m = a.m; p.div_wrv_s = a.s; p.div_rv_m = b.m; p.div_rv_s = b.s;
+    // token ids / per-token scalars into a padded batch: four consecutive vectors per thread, one wide store
+    if (srck == RUA_CAT && p.row_vecs == 1 && p.d.width >= 4 && p.d.width <= (1ll << 30) &&
+        ((uintptr_t)p.dst & (4 * sizeof(V) - 1)) == 0) {
+      row_map_padded_cat1_kernel<V><<<nb, kTileThreads, 0, st>>>(p);
+      return;
+    }
     switch (srck) {
       case RUA_CAT: row_map_padded_kernel<V, RUA_CAT><<<nb, kTileThreads, 0, st>>>(p); break;
       case RUA_LEFT: row_map_padded_kernel<V, RUA_LEFT><<<nb, kTileThreads, 0, st>>>(p); break;

@@ -550,6 +550,90 @@ __device__ __forceinline__ void tile_body(const RowMapParams& p, OffFn f, int64_
   }
 }
 
+// four consecutive vectors as one wide store (256-bit for 8-byte vectors: a full sector per lane)
+template <typename V> __device__ __forceinline__ void store4(V* p, const V& a, const V& b, const V& c, const V& d) {
+  st_stream(p, a); st_stream(p + 1, b); st_stream(p + 2, c); st_stream(p + 3, d);
+}
+template <> __device__ __forceinline__ void store4<uint2>(uint2* p, const uint2& a, const uint2& b, const uint2& c, const uint2& d) {
+  auto u64 = [](const uint2& v) { return ((unsigned long long)v.y << 32) | v.x; };
+  st_stream(reinterpret_cast<V256*>(p), V256{u64(a), u64(b), u64(c), u64(d)});
+}
+template <> __device__ __forceinline__ void store4<unsigned int>(unsigned int* p, const unsigned int& a, const unsigned int& b,
+                                                                 const unsigned int& c, const unsigned int& d) {
+  st_stream(reinterpret_cast<uint4*>(p), make_uint4(a, b, c, d));
+}
+template <> __device__ __forceinline__ void store4<uint4>(uint4* p, const uint4& a, const uint4& b, const uint4& c, const uint4& d) {
+  auto u64 = [](unsigned lo, unsigned hi) { return ((unsigned long long)hi << 32) | lo; };
+  st_stream(reinterpret_cast<V256*>(p), V256{u64(a.x, a.y), u64(a.z, a.w), u64(b.x, b.y), u64(b.z, b.w)});
+  st_stream(reinterpret_cast<V256*>(p) + 1, V256{u64(c.x, c.y), u64(c.z, c.w), u64(d.x, d.y), u64(d.z, d.w)});
+}
+
+// L / R -> C, C.rev, C.roll with ONE-VECTOR rows: the same idea as row_map_padded_cat1_kernel on the decoded tile --
+// a thread owns four consecutive rows of C, reads their segment indices with one 128-bit shared-memory load, resolves
+// the segment once (twice when the group crosses a boundary), loads four vectors and stores them as one wide store.
+template <typename V, int SRC>
+__global__ void __launch_bounds__(kTileThreads)
+row_map_tile_cat1_kernel(const RowMapParams p) {
+  __shared__ TileDecodeSmem sm;
+  const int tid = threadIdx.x;
+  const int64_t total = p.d.rows;
+  const int64_t e0 = (int64_t)blockIdx.x * kTileVecs;
+  const int n_e = (int)(e0 + kTileVecs < total ? kTileVecs : total - e0);
+  GlobalOff f{p.rg.off};
+  const TileDecode dec = tile_decode(f, p.rg.B, e0, n_e, sm);
+  const V* __restrict__ src = reinterpret_cast<const V*>(p.src);
+  V* __restrict__ dst = reinterpret_cast<V*>(p.dst) + e0;
+  const int64_t W = p.s.width;
+#pragma unroll
+  for (int g = 0; g < kTileItems / 4; ++g) {
+    const int eb = (g * kTileThreads + tid) * 4;
+    if (eb >= n_e) break;
+    int kk[4];
+    if (dec.staged) {
+      const int4 k4 = reinterpret_cast<const int4*>(sm.seg)[eb >> 2];
+      kk[0] = k4.x; kk[1] = k4.y; kk[2] = k4.z; kk[3] = k4.w;
+    } else {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) kk[j] = (int)(owner_search(f, p.rg.B, e0 + (eb + j < n_e ? eb + j : n_e - 1)) - dec.first);
+    }
+    int64_t srow[4];
+    int k_prev = -1;
+    int64_t base = 0, len = 0, i = 0;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int k = kk[j];
+      if (k != k_prev) {                       // a group rarely crosses a boundary: one lookup for all four
+        k_prev = k;
+        i = dec.first + k;
+        if (dec.staged && k > 0) {
+          const int r = sm.rel[k], nx = sm.rel[k + 1];
+          base = e0 + r;
+          len = nx <= kTileVecs ? (int64_t)(nx - r) : __ldg(p.rg.off + i + 1) - base;
+        } else {
+          base = __ldg(p.rg.off + i);
+          len = __ldg(p.rg.off + i + 1) - base;
+        }
+      }
+      const int64_t td = e0 + eb + j - base;
+      if (SRC == RUA_LEFT) srow[j] = i * W + td;
+      else if (SRC == RUA_RIGHT) srow[j] = i * W + (W - len) + td;
+      else if (SRC == kSrcCatRev) srow[j] = base + (len - 1 - td);
+      else { const int64_t m = (td - p.tmap_arg) % len; srow[j] = base + (m < 0 ? m + len : m); }
+    }
+    V v[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      if (eb + j < n_e) v[j] = ld_stream(src + srow[j]);
+    if (eb + 4 <= n_e) {
+      store4<V>(dst + eb, v[0], v[1], v[2], v[3]);
+    } else {
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        if (eb + j < n_e) st_stream(dst + eb + j, v[j]);
+    }
+  }
+}
+
 // destination C or P: segment search through shared memory
 template <typename V, int SRC>
 __global__ void __launch_bounds__(kTileThreads)
@@ -692,23 +776,6 @@ row_map_padded_kernel(const RowMapParams p) {
 // kernel above decodes every 8-byte element on its own (fast division, two shared-memory reads, validity test) and is
 // issue-bound at 72 % issue-active.  Here a thread owns FOUR consecutive destination vectors: one division, one pair of
 // shared-memory reads (two when the group straddles a row end), four loads, ONE wide store.
-template <typename V> __device__ __forceinline__ void store4(V* p, const V& a, const V& b, const V& c, const V& d) {
-  st_stream(p, a); st_stream(p + 1, b); st_stream(p + 2, c); st_stream(p + 3, d);
-}
-template <> __device__ __forceinline__ void store4<uint2>(uint2* p, const uint2& a, const uint2& b, const uint2& c, const uint2& d) {
-  auto u64 = [](const uint2& v) { return ((unsigned long long)v.y << 32) | v.x; };
-  st_stream(reinterpret_cast<V256*>(p), V256{u64(a), u64(b), u64(c), u64(d)});
-}
-template <> __device__ __forceinline__ void store4<unsigned int>(unsigned int* p, const unsigned int& a, const unsigned int& b,
-                                                                 const unsigned int& c, const unsigned int& d) {
-  st_stream(reinterpret_cast<uint4*>(p), make_uint4(a, b, c, d));
-}
-template <> __device__ __forceinline__ void store4<uint4>(uint4* p, const uint4& a, const uint4& b, const uint4& c, const uint4& d) {
-  auto u64 = [](unsigned lo, unsigned hi) { return ((unsigned long long)hi << 32) | lo; };
-  st_stream(reinterpret_cast<V256*>(p), V256{u64(a.x, a.y), u64(a.z, a.w), u64(b.x, b.y), u64(b.z, b.w)});
-  st_stream(reinterpret_cast<V256*>(p) + 1, V256{u64(c.x, c.y), u64(c.z, c.w), u64(d.x, d.y), u64(d.z, d.w)});
-}
-
 template <typename V>
 __global__ void __launch_bounds__(kTileThreads)
 row_map_padded_cat1_kernel(const RowMapParams p) {
@@ -940,6 +1007,17 @@ static void launch_narrow(RowMapParams& p, int64_t rows, cudaStream_t st) {
   const int srck = simple ? p.s.layout : (cat_select ? (p.tmap == RUA_MAP_REV ? kSrcCatRev : kSrcCatRoll) : kGenericSrc);
   const unsigned nb = (unsigned)blocks;
   if (searched) {
+    // one-vector rows into C from L / R, and C.rev / C.roll: four consecutive rows per thread, one wide store
+    if (p.d.layout == RUA_CAT && p.row_vecs == 1 && ((uintptr_t)p.dst & (4 * sizeof(V) - 1)) == 0 &&
+        (srck == RUA_LEFT || srck == RUA_RIGHT || srck == kSrcCatRev || srck == kSrcCatRoll)) {
+      switch (srck) {
+        case RUA_LEFT: row_map_tile_cat1_kernel<V, RUA_LEFT><<<nb, kTileThreads, 0, st>>>(p); break;
+        case RUA_RIGHT: row_map_tile_cat1_kernel<V, RUA_RIGHT><<<nb, kTileThreads, 0, st>>>(p); break;
+        case kSrcCatRev: row_map_tile_cat1_kernel<V, kSrcCatRev><<<nb, kTileThreads, 0, st>>>(p); break;
+        default: row_map_tile_cat1_kernel<V, kSrcCatRoll><<<nb, kTileThreads, 0, st>>>(p); break;
+      }
+      return;
+    }
     switch (srck) {
       case RUA_CAT: row_map_tile_kernel<V, RUA_CAT><<<nb, kTileThreads, 0, st>>>(p); break;
       case RUA_LEFT: row_map_tile_kernel<V, RUA_LEFT><<<nb, kTileThreads, 0, st>>>(p); break;

@@ -779,26 +779,29 @@ row_map_padded_kernel(const RowMapParams p) {
 template <typename V>
 __global__ void __launch_bounds__(kTileThreads)
 row_map_padded_cat1_kernel(const RowMapParams p) {
-  __shared__ int s_rel[kTileCap];            // off[i0 + k] - off[i0]
+  // A sequence of C is one contiguous run of len * rv vectors and lands in one contiguous run of its padded row, so
+  // rows of several vectors are handled by SCALING: widths, lengths and offsets are counted in vectors.
+  __shared__ int s_rel[kTileCap];            // (off[i0 + k] - off[i0]) * rv
   const int tid = threadIdx.x;
-  const int64_t total = p.d.rows;             // one vector per row
+  const int rv = (int)p.row_vecs;
+  const int64_t total = p.d.rows * rv;
   const int64_t e0 = (int64_t)blockIdx.x * kTileVecs;
   const int n_e = (int)(e0 + kTileVecs < total ? kTileVecs : total - e0);
-  const uint32_t W = (uint32_t)p.d.width;     // 4 <= W <= 2^30 (checked by the launcher)
+  const uint32_t W = (uint32_t)(p.d.width * rv);   // vectors per padded row: 4 <= W <= 2^30 (checked by the launcher)
   const int64_t i0 = e0 / W;
   const int64_t i1 = (e0 + n_e - 1) / W;
   const uint32_t head = (uint32_t)(e0 - i0 * W);
   const int cnt = (int)(i1 - i0 + 2);
   const int64_t base0 = __ldg(p.rg.off + i0);
   for (int k = tid; k < cnt; k += kTileThreads) {
-    const int64_t d = __ldg(p.rg.off + i0 + k) - base0;
+    const int64_t d = (__ldg(p.rg.off + i0 + k) - base0) * rv;
     s_rel[k] = d > (1 << 30) ? (1 << 30) : (int)d;
   }
   __syncthreads();
   const bool right_dst = p.d.layout == RUA_RIGHT;
-  const V* __restrict__ src = reinterpret_cast<const V*>(p.src) + base0;
+  const V* __restrict__ src = reinterpret_cast<const V*>(p.src) + base0 * rv;
   V* __restrict__ dst = reinterpret_cast<V*>(p.dst) + e0;
-  const V fill = make_fill<V>(p.fill, 0);
+  const V fill = make_fill<V>(p.fill, 0);    // the launcher checked that the fill pattern has period sizeof(V)
 #pragma unroll
   for (int g = 0; g < kTileItems / 4; ++g) {
     const int eb = (g * kTileThreads + tid) * 4;          // tile-relative, 4 consecutive destination vectors
@@ -809,7 +812,7 @@ row_map_padded_cat1_kernel(const RowMapParams p) {
     int sq = s_rel[q], len = s_rel[q + 1] - sq;
     int shift = right_dst ? (int)W - len : 0;
     V v[4];
-    int from[4];                                          // source vector relative to base0, or -1 = padding
+    int from[4];                                          // source vector relative to base0 * rv, or -1 = padding
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       int t = (int)rem + j;
@@ -1031,8 +1034,14 @@ static void launch_narrow(RowMapParams& p, int64_t rows, cudaStream_t st) {
     const int64_t wrv = p.d.width * p.row_vecs;
     const FastDiv a = FastDiv::make((uint64_t)(wrv > (1ll << 30) ? 1 : wrv)), b = FastDiv::make((uint64_t)p.row_vecs);
     p.div_wrv_m = a.m; p.div_wrv_s = a.s; p.div_rv_m = b.m; p.div_rv_s = b.s;
-    // token ids / per-token scalars into a padded batch: four consecutive vectors per thread, one wide store
-    if (srck == RUA_CAT && p.row_vecs == 1 && p.d.width >= 4 && p.d.width <= (1ll << 30) &&
+    // C into a padded batch (token ids, per-token scalars, small feature rows): four consecutive vectors per thread,
+    // one wide store.  Needs a fill pattern that looks the same in every vector of a row.
+    bool fill_periodic = true;
+    {
+      const unsigned char* fb = reinterpret_cast<const unsigned char*>(&p.fill);
+      for (size_t k = sizeof(V); k < 16; ++k) fill_periodic &= fb[k] == fb[k % sizeof(V)];
+    }
+    if (srck == RUA_CAT && fill_periodic && wrv >= 4 && wrv <= (1ll << 30) &&
         ((uintptr_t)p.dst & (4 * sizeof(V) - 1)) == 0) {
       row_map_padded_cat1_kernel<V><<<nb, kTileThreads, 0, st>>>(p);
       return;

@@ -571,19 +571,28 @@ template <> __device__ __forceinline__ void store4<uint4>(uint4* p, const uint4&
 // L / R -> C, C.rev, C.roll with ONE-VECTOR rows: the same idea as row_map_padded_cat1_kernel on the decoded tile --
 // a thread owns four consecutive rows of C, reads their segment indices with one 128-bit shared-memory load, resolves
 // the segment once (twice when the group crosses a boundary), loads four vectors and stores them as one wide store.
+struct ScaledOff {   // offsets counted in vectors: a sequence of C is one contiguous run of len * rv vectors
+  const int64_t* __restrict__ p;
+  int64_t rv;
+  __device__ __forceinline__ int64_t operator()(int64_t i) const { return __ldg(p + i) * rv; }
+};
+
 template <typename V, int SRC>
 __global__ void __launch_bounds__(kTileThreads)
 row_map_tile_cat1_kernel(const RowMapParams p) {
   __shared__ TileDecodeSmem sm;
   const int tid = threadIdx.x;
-  const int64_t total = p.d.rows;
+  // L / R sources: positions, offsets, lengths and widths are all counted in VECTORS (rows of several vectors are
+  // contiguous on both sides); rev / roll permute tokens and run with one vector per row only (rv == 1)
+  const int64_t rv = (SRC == RUA_LEFT || SRC == RUA_RIGHT) ? p.row_vecs : 1;
+  const int64_t total = p.d.rows * rv;
   const int64_t e0 = (int64_t)blockIdx.x * kTileVecs;
   const int n_e = (int)(e0 + kTileVecs < total ? kTileVecs : total - e0);
-  GlobalOff f{p.rg.off};
+  ScaledOff f{p.rg.off, rv};
   const TileDecode dec = tile_decode(f, p.rg.B, e0, n_e, sm);
   const V* __restrict__ src = reinterpret_cast<const V*>(p.src);
   V* __restrict__ dst = reinterpret_cast<V*>(p.dst) + e0;
-  const int64_t W = p.s.width;
+  const int64_t W = p.s.width * rv;
 #pragma unroll
   for (int g = 0; g < kTileItems / 4; ++g) {
     const int eb = (g * kTileThreads + tid) * 4;
@@ -608,10 +617,10 @@ row_map_tile_cat1_kernel(const RowMapParams p) {
         if (dec.staged && k > 0) {
           const int r = sm.rel[k], nx = sm.rel[k + 1];
           base = e0 + r;
-          len = nx <= kTileVecs ? (int64_t)(nx - r) : __ldg(p.rg.off + i + 1) - base;
+          len = nx <= kTileVecs ? (int64_t)(nx - r) : f(i + 1) - base;
         } else {
-          base = __ldg(p.rg.off + i);
-          len = __ldg(p.rg.off + i + 1) - base;
+          base = f(i);
+          len = f(i + 1) - base;
         }
       }
       const int64_t td = e0 + eb + j - base;
@@ -998,7 +1007,7 @@ static void launch_narrow(RowMapParams& p, int64_t rows, cudaStream_t st) {
     }
     return;
   }
-  const int64_t blocks = ceil_div(rows * p.row_vecs, kTileVecs);
+  const int64_t blocks = ceil_div(rows * p.row_vecs, kTileVecs);   // tiles of 2048 destination vectors
   const bool indexed = p.gather_index || p.scatter_index;
   const bool searched = !indexed && (p.d.layout == RUA_CAT || p.d.layout == RUA_PACK);
   // the 12 conversions (identity token map, untransformed lengths, plain fill) run source-specialised code
@@ -1011,8 +1020,8 @@ static void launch_narrow(RowMapParams& p, int64_t rows, cudaStream_t st) {
   const unsigned nb = (unsigned)blocks;
   if (searched) {
     // one-vector rows into C from L / R, and C.rev / C.roll: four consecutive rows per thread, one wide store
-    if (p.d.layout == RUA_CAT && p.row_vecs == 1 && ((uintptr_t)p.dst & (4 * sizeof(V) - 1)) == 0 &&
-        (srck == RUA_LEFT || srck == RUA_RIGHT || srck == kSrcCatRev || srck == kSrcCatRoll)) {
+    if (p.d.layout == RUA_CAT && ((uintptr_t)p.dst & (4 * sizeof(V) - 1)) == 0 &&
+        (srck == RUA_LEFT || srck == RUA_RIGHT || (p.row_vecs == 1 && (srck == kSrcCatRev || srck == kSrcCatRoll)))) {
       switch (srck) {
         case RUA_LEFT: row_map_tile_cat1_kernel<V, RUA_LEFT><<<nb, kTileThreads, 0, st>>>(p); break;
         case RUA_RIGHT: row_map_tile_cat1_kernel<V, RUA_RIGHT><<<nb, kTileThreads, 0, st>>>(p); break;

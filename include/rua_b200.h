@@ -98,6 +98,8 @@ const char* rua_error_string(int status);
 int rua_last_cuda_error(void);
 /* number of kernel launches issued by this library since load (for bench.py's gpu_launches) */
 int64_t rua_launch_count(void);
+/* host-only self test of launch-time arithmetic (magic-number division of the narrow-row kernels): 0 = ok.  No GPU. */
+int rua_selftest(void);
 
 /* ------------------------------------------------------------------------------------------- */
 /* K0  metadata from lengths                                                                     */

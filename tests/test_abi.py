@@ -52,7 +52,22 @@ def test_host_only_entry_points(lib):
     assert lib.rua_scan_lengths(None, -1, 0, None, None, None, 0, None) == -1
     assert lib.rua_segment_reduce(None, None, -1, 0, 0, 0, 0, None, None, 0, None) == -1
     assert lib.rua_mask(None, -1, 0, None, None, 1, None, None) == -1
+    # the entry points added for parity mode, list constructors and the multi-GPU gather validate the same way
+    assert lib.rua_segment_reduce_strict(None, None, -1, 0, 0, 0, 0, None, None) == -1
+    assert lib.rua_segment_reduce_strict(None, None, 4, 2, 8, 0, 3, None, None) == -1          # null buffers
+    assert lib.rua_scatter_rows_multi(None, None, -1, 8, None, 1, None) == -1
+    assert lib.rua_scatter_rows_multi(None, None, 4, 8, None, 99, None) == -1                   # too many destinations
+    assert lib.rua_row_map_multi(None, 8, None, None, 4, None, None, 1, None) == -1
+    assert lib.rua_row_map_list(None, 16, None, 8, None, None, None, 0, None) == -1
+    assert lib.rua_peer_window_alloc(0, None, None) == -1
+    assert lib.rua_peer_window_open(None, None) == -1
     assert lib.rua_launch_count() == 0
+
+
+def test_host_side_selftest(lib):
+    """launch-time arithmetic of the narrow-row kernels (magic-number division, exact for every x < 2^31): checked on
+    the host by the library itself, no GPU involved."""
+    assert lib.rua_selftest() == 0
 
 
 def test_api_surface_matches_reference():

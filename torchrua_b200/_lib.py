@@ -35,6 +35,7 @@ SIGNATURES = {
     'rua_error_string': (c_char_p, [c_int32]),
     'rua_last_cuda_error': (c_int32, []),
     'rua_launch_count': (c_int64, []),
+    'rua_selftest': (c_int32, []),
     'rua_scan_workspace_bytes': (c_size_t, [c_int64]),
     'rua_scan_lengths': (c_int32, [c_void_p, c_int64, c_int64, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
     'rua_sort_workspace_bytes': (c_size_t, [c_int64]),

@@ -1338,4 +1338,37 @@ int rua_row_map_list(const void* const* src_list, int32_t src_align, void* dst, 
   return launch_row_map_list(p, (const uint8_t* const*)src_list, src_align, row_bytes, dst_side->rows, (cudaStream_t)stream);
 }
 
+/* host-only self test of the launch-time arithmetic (no GPU needed; run by the CPU test-suite): the magic-number
+ * division the narrow-row kernels use must be exact for every x < 2^31.  Returns 0, or the failing divisor negated. */
+int rua_selftest(void) {
+  unsigned long long state = 0x9e3779b97f4a7c15ull;
+  auto next = [&state]() { state ^= state << 13; state ^= state >> 7; state ^= state << 17; return state; };
+  auto check = [](uint64_t d) -> bool {
+    const FastDiv f = FastDiv::make(d);
+    const uint64_t xs[] = {0, 1, d - 1, d, d + 1, 2 * d - 1, 2 * d, 3 * d + 1, (1ull << 31) - 1, (1ull << 31) - d,
+                           (1ull << 30), (1ull << 30) + d - 1, ((1ull << 31) - 1) / d * d, ((1ull << 31) - 1) / d * d - 1};
+    for (uint64_t x : xs) {
+      if (x >= (1ull << 31)) continue;
+      if ((uint32_t)((x * f.m) >> f.s) != (uint32_t)(x / d)) return false;
+    }
+    return true;
+  };
+  for (uint64_t d = 1; d <= 70000; ++d)
+    if (!check(d)) return -(int)d;
+  for (int b = 1; b <= 30; ++b)
+    for (int64_t delta = -2; delta <= 2; ++delta) {
+      const int64_t d = (1ll << b) + delta;
+      if (d >= 1 && d <= (1ll << 30) && !check((uint64_t)d)) return -(int)d;
+    }
+  for (int k = 0; k < 200000; ++k) {
+    const uint64_t d = 1 + next() % (1ull << 30);
+    const FastDiv f = FastDiv::make(d);
+    for (int j = 0; j < 8; ++j) {
+      const uint64_t x = next() % (1ull << 31);
+      if ((uint32_t)((x * f.m) >> f.s) != (uint32_t)(x / d)) return -(int)d;
+    }
+  }
+  return 0;
+}
+
 }  // extern "C"

@@ -176,12 +176,29 @@ int rua_row_map_list(const void* const* src_list, int32_t src_align, void* dst, 
                      int32_t fill_bytes, rua_stream_t stream);
 
 /* dst[j] = src[index[j]] for j < n   (tensor_getitem / Z-keyed getitem, core/get.py:11-31).
- * Negative indices wrap (index + src_rows) like torch advanced indexing. */
+ * Negative indices wrap (index + src_rows) like torch advanced indexing; an index that is still out of range is
+ * not dereferenced: the row is zero-filled (gather) or skipped (scatter) and counted (rua_index_error_count). */
 int rua_gather_rows(const void* src, int64_t src_rows, const int64_t* index, int64_t n,
                     int64_t row_bytes, void* dst, rua_stream_t stream);
 /* dst[index[j]] = src[j] for j < n   (tensor_setitem / Z-keyed setitem, core/set.py:10-31) */
 int rua_scatter_rows(const void* src, const int64_t* index, int64_t n, int64_t row_bytes, void* dst,
                      int64_t dst_rows, rua_stream_t stream);
+
+/* flat storage rows of layout position keys -- the (batch_ptr, token_ptr) branches of
+ * {cat,left,pack,right}_getitem / _setitem (torchrua/core/get.py:21-82, core/set.py:23-92):
+ *   C: min(off[b], rows-1) + t     L: b*W + t     R: b*W + (T - len[b]) + t     P: unsorted[b] + min(poff[t], rows-1)
+ * with the clamps of C.offsets() / P.offsets() (layout/cat.py:79-81, pack.py:43-45), T = max length for R
+ * (layout/right.py:62-67: size()[1], not the storage width W = side->width) and torch's wrap-around of negative
+ * indices where the reference's indexing applies it.  batch_ptr == NULL: token_ptr holds flat rows already; they
+ * are wrapped and bounds-checked only.  Out-of-range keys yield side->rows (one past the end: rua_gather_rows zero-fills it,
+ * rua_scatter_rows skips it, an ascending sort keeps it last) and bump the error counter below.  Feed rows_out to rua_gather_rows / rua_scatter_rows. */
+int rua_token_rows(const rua_ragged_t* ragged, const rua_side_t* side, int64_t T, const int64_t* batch_ptr,
+                   const int64_t* token_ptr, int64_t n, int64_t* rows_out, rua_stream_t stream);
+
+/* number of out-of-range indices seen by rua_gather_rows / rua_scatter_rows / rua_token_rows on the current device
+ * since the last reset.  Those rows were NOT dereferenced (ATen device-asserts in the same situation).  This call
+ * synchronises (one 8-byte device->host copy): diagnostics, not data path. */
+int rua_index_error_count(int64_t* count_host, int32_t reset);
 
 /* ------------------------------------------------------------------------------------------- */
 /* K3  mask / index emit (no payload reads)                                                      */

@@ -56,6 +56,8 @@ SIGNATURES = {
                                    c_int32, c_void_p]),
     'rua_gather_rows': (c_int32, [c_void_p, c_int64, c_void_p, c_int64, c_int64, c_void_p, c_void_p]),
     'rua_scatter_rows': (c_int32, [c_void_p, c_void_p, c_int64, c_int64, c_void_p, c_int64, c_void_p]),
+    'rua_token_rows': (c_int32, [POINTER(Ragged), POINTER(Side), c_int64, c_void_p, c_void_p, c_int64, c_void_p, c_void_p]),
+    'rua_index_error_count': (c_int32, [POINTER(c_int64), c_int32]),
     'rua_mask': (c_int32, [c_void_p, c_int64, c_int64, c_char_p, c_char_p, c_int32, c_void_p, c_void_p]),
     'rua_emit_ptr': (c_int32, [c_void_p, c_int64, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_int64,
                                c_int32, c_void_p]),

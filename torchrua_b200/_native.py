@@ -14,7 +14,7 @@ from torch import Tensor
 
 from torchrua_b200 import _lib
 from torchrua_b200._lib import (CAT, LEFT, LEN_CONST, LEN_MINUS, LEN_SAME, MAP_REV, MAP_ROLL, MAP_SHIFT, PACK,
-                                PAD_FILL, PAD_ROW0, RIGHT)
+                                PAD_FILL, PAD_ROW0, PAD_WRAP, RIGHT)
 
 _DTYPES = {torch.float32: _lib.F32, torch.float64: _lib.F64, torch.float16: _lib.F16, torch.bfloat16: _lib.BF16}
 _OPS = {'sum': _lib.SUM, 'mean': _lib.MEAN, 'prod': _lib.PROD, 'max': _lib.MAX, 'min': _lib.MIN,
@@ -183,6 +183,15 @@ class Ragged:
     Tp: int = 0
     _keep: list = field(default_factory=list)
     _spec_ok: bool = False            # the speculative early launch of _ensure_pack_fused held
+    _event: Optional[torch.cuda.Event] = None   # recorded after the producer kernels, on _stream (see _cache_get)
+    _stream: int = 0
+
+    def mark_ready(self):
+        with _on(self.device):
+            st = torch.cuda.current_stream()
+            self._stream = st.cuda_stream
+            self._event = torch.cuda.Event()
+            self._event.record(st)
 
     def _sync_stats(self):
         # the one inherent D2H: output shapes depend on device data (16 bytes, pinned, stream-ordered)
@@ -281,11 +290,22 @@ _CACHE_LIMIT = 64
 
 
 def _cache_get(key_tensor: Tensor, tag: str):
+    """Entries are keyed on the tensor OBJECT and its version counter: in-place writes through torch (and through this
+    package's own scatter, which bumps the counter) invalidate them; writes through a raw pointer that bypass the
+    counter (another framework, a C extension) do not -- call ``clear_metadata_cache()`` after those.
+
+    The cached device arrays were produced on the stream that was current when the entry was built; a consumer on
+    ANOTHER stream waits for the event recorded there before it launches anything that reads them."""
     ent = _CACHE.get((id(key_tensor), tag))
     if ent is None:
         return None
     ref, version, value = ent
     if ref() is key_tensor and key_tensor._version == version:
+        ev = getattr(value, '_event', None)
+        if ev is not None:
+            cur = torch.cuda.current_stream(value.device)
+            if cur.cuda_stream != value._stream:
+                cur.wait_event(ev)
         return value
     del _CACHE[(id(key_tensor), tag)]
     return None
@@ -294,7 +314,13 @@ def _cache_get(key_tensor: Tensor, tag: str):
 def _cache_put(key_tensor: Tensor, tag: str, value):
     if len(_CACHE) >= _CACHE_LIMIT:
         _CACHE.pop(next(iter(_CACHE)))
+    if isinstance(value, Ragged):
+        value.mark_ready()
     _CACHE[(id(key_tensor), tag)] = (weakref.ref(key_tensor), key_tensor._version, value)
+
+
+def clear_metadata_cache() -> None:
+    _CACHE.clear()
 
 
 FUSED_MAX_B = 8192   # == rua_meta_fused_max_batch()
@@ -337,6 +363,9 @@ def ragged_from_pack(batch_sizes: Tensor, sorted_indices: Optional[Tensor], unso
         bs_cpu = bs_cpu.cpu()
     bs_cpu = bs_cpu.long().contiguous()
     Tp = bs_cpu.numel()
+    total = int(bs_cpu.sum()) if Tp else 0
+    if n_rows >= 0 and total != n_rows:   # host-only check: inconsistent metadata would index past the payload
+        raise RuntimeError(f'torchrua_b200: PackedSequence has {n_rows} rows of data but batch_sizes sums to {total}')
     # B counts every sequence, including empty ones that never show up in batch_sizes
     B = unsorted_indices.numel() if unsorted_indices is not None else (int(bs_cpu[0]) if Tp > 0 else 0)
     with _on(device):
@@ -461,8 +490,18 @@ class _RowMap(torch.autograd.Function):
     @staticmethod
     def backward(ctx, grad_out: Tensor):
         spec: MapSpec = ctx.spec
-        inv = spec.inverse()
         g = grad_out.contiguous()
+        if spec.pad_mode == PAD_WRAP and ctx.src_rows > 0 and g.shape[0] > 0 and g.dtype in _DTYPES:
+            # last() / segment_last of an EMPTY sequence read a wrapped row in the forward pass (select/last.py:11-13),
+            # so one source row can feed several outputs and the inverse map is not a map.  Push the source row
+            # numbers through the forward map instead and sum the gradient rows per source row (stable device sort +
+            # one gathered segment-sum launch: deterministic, no atomics); fill = one-past-the-end = dropped bucket.
+            rows = ctx.src_rows
+            ids = torch.arange(rows, dtype=torch.long, device=g.device)
+            where = _row_map_raw(ids, spec, int(rows).to_bytes(8, 'little'), (), torch.long, g.device)
+            red, _ = scatter_reduce(g, where, rows + 1, 'sum')
+            return red[:rows], None, None
+        inv = spec.inverse()
         zero = bytes(g.element_size())
         grad_src = _row_map_raw(g, inv, zero, tuple(g.shape[1:]), g.dtype, g.device)
         if spec.pad_mode == PAD_ROW0 and grad_src.shape[0] > 0:
@@ -646,40 +685,105 @@ def new_from_list(tensors, layout: int, fill_value, plan):
     return out, rg
 
 
+def index_errors(reset: bool = True) -> int:
+    """out-of-range indices seen by the gather / scatter / position-key kernels on the current device since the last
+    reset (those rows were zero-filled / skipped, never dereferenced).  Synchronises; diagnostics only."""
+    lib = _lib.load()
+    n = ctypes.c_int64(0)
+    _lib.check(lib.rua_index_error_count(ctypes.byref(n), int(reset)), 'rua_index_error_count')
+    return int(n.value)
+
+
+def token_rows(rg: Optional[Ragged], side: 'SideSpec', T: int, batch_ptr: Optional[Tensor], token_ptr: Tensor) -> Tensor:
+    """flat storage rows of (batch_ptr, token_ptr) position keys in the layout described by ``side`` (core/get.py:21-82);
+    ``batch_ptr=None``: ``token_ptr`` holds flat rows, which are wrapped (negative indices) and bounds-checked."""
+    lib = _lib.load()
+    if batch_ptr is not None:
+        if batch_ptr.shape != token_ptr.shape:
+            batch_ptr, token_ptr = torch.broadcast_tensors(batch_ptr, token_ptr)
+        b = _i64(batch_ptr)
+    t = _i64(token_ptr)
+    out = torch.empty(t.shape, dtype=torch.long, device=t.device)
+    if out.numel() > 0:
+        sd = side.c_struct()
+        rgc = rg.c_struct() if batch_ptr is not None else None
+        with _on(t.device):
+            _lib.check(lib.rua_token_rows(ctypes.byref(rgc) if rgc is not None else None, ctypes.byref(sd), T,
+                                          b.data_ptr() if batch_ptr is not None else None, t.data_ptr(), t.numel(),
+                                          out.data_ptr(), _stream()), 'rua_token_rows')
+    return out
+
+
+def _gather_rows_raw(flat: Tensor, idx: Tensor) -> Tensor:
+    """flat (rows, *feat) contiguous, idx int64 contiguous of any shape -> (idx.numel(), *feat)."""
+    lib = _lib.load()
+    out = torch.empty((idx.numel(),) + tuple(flat.shape[1:]), dtype=flat.dtype, device=flat.device)
+    if out.numel() > 0:
+        row_bytes = flat.element_size() * (flat[0].numel() if flat.shape[0] else 0)
+        with _on(flat.device):
+            _lib.check(lib.rua_gather_rows(flat.data_ptr(), flat.shape[0], idx.data_ptr(), idx.numel(),
+                                           row_bytes, out.data_ptr(), _stream()), 'rua_gather_rows')
+    return out
+
+
+def _scatter_rows_raw(dst: Tensor, idx: Tensor, val: Tensor) -> None:
+    """dst (rows, *feat) contiguous, idx (n,) int64, val (n, *feat) contiguous: dst[idx[j]] = val[j]."""
+    lib = _lib.load()
+    if val.numel() == 0:
+        return
+    row_bytes = dst.element_size() * (dst[0].numel())
+    with _on(dst.device):
+        _lib.check(lib.rua_scatter_rows(val.data_ptr(), idx.data_ptr(), idx.numel(), row_bytes, dst.data_ptr(),
+                                        dst.shape[0], _stream()), 'rua_scatter_rows')
+
+
 class _GatherRows(torch.autograd.Function):
     @staticmethod
     def forward(ctx, src: Tensor, index: Tensor):
-        lib = _lib.load()
         idx = _i64(index)
         ctx.save_for_backward(idx)
         ctx.src_shape = src.shape
         flat = src.detach().contiguous()
-        out = torch.empty((idx.numel(),) + tuple(flat.shape[1:]), dtype=flat.dtype, device=flat.device)
-        if out.numel() > 0:
-            row_bytes = flat.element_size() * (flat[0].numel() if flat.shape[0] else 0)
-            with _on(flat.device):
-                _lib.check(lib.rua_gather_rows(flat.data_ptr(), flat.shape[0], idx.data_ptr(), idx.numel(),
-                                               row_bytes, out.data_ptr(), _stream()), 'rua_gather_rows')
+        out = _gather_rows_raw(flat, idx)
         return out.view(tuple(index.shape) + tuple(flat.shape[1:]))
 
     @staticmethod
     def backward(ctx, grad_out: Tensor):
         (idx,) = ctx.saved_tensors
-        # arbitrary user indices may repeat: accumulate (deterministic sort-based ATen path; not on the
-        # hot path -- casts and selects never come through here)
-        grad = torch.zeros(ctx.src_shape, dtype=grad_out.dtype, device=grad_out.device)
-        grad.index_put_((idx.view(-1),), grad_out.reshape((-1,) + tuple(ctx.src_shape[1:])), accumulate=True)
+        rows = ctx.src_shape[0]
+        feat = tuple(ctx.src_shape[1:])
+        if idx.numel() == 0 or rows == 0:
+            return torch.zeros(ctx.src_shape, dtype=grad_out.dtype, device=grad_out.device), None
+        # user indices may repeat: the gradient of a row is the SUM over its occurrences.  Native and deterministic:
+        # normalise the indices (wrap + bounds; out-of-range ones go to an extra bucket `rows`), stable device sort,
+        # then one segment-reduce launch that gathers grad rows in sorted order (no atomics; fp32 accumulation).
+        norm = token_rows(None, SideSpec(CAT, rows=rows), 0, None, idx.view(-1))
+        g = grad_out.reshape((-1,) + feat)
+        if g.dtype in _DTYPES:
+            red, _ = scatter_reduce(g if g.is_contiguous() else g.contiguous(), norm, rows + 1, 'sum')
+            return red[:rows], None
+        grad = torch.zeros(ctx.src_shape, dtype=grad_out.dtype, device=grad_out.device)   # integer / complex grads: ATen
+        grad.index_put_((norm.clamp_max(rows - 1),), g, accumulate=True)
         return grad, None
 
 
 def gather_rows(src: Tensor, index: Tensor) -> Tensor:
     require_cuda(src, index)
+    if not (src.requires_grad and torch.is_grad_enabled()):
+        flat = src.detach()
+        if not flat.is_contiguous():
+            flat = flat.contiguous()
+        return _gather_rows_raw(flat, _i64(index)).view(tuple(index.shape) + tuple(flat.shape[1:]))
     return _GatherRows.apply(src, index)
 
 
-def scatter_rows_(dst: Tensor, index: Tensor, value: Tensor) -> None:
-    """dst[index[j]] = value[j] in place (no autograd; mirrors Tensor.__setitem__ on .data)."""
-    lib = _lib.load()
+def _bump_version(t: Tensor) -> None:
+    """a write through the raw pointer is invisible to autograd's and this package's own version checks."""
+    torch.autograd.graph.increment_version(t)
+
+
+def scatter_rows_(dst: Tensor, index: Tensor, value) -> None:
+    """dst[index[j]] = value[j] in place, outside autograd (the tracked case is _ScatterRows)."""
     require_cuda(dst, index)
     if not dst.is_contiguous():
         raise RuntimeError('torchrua_b200: in-place scatter needs a contiguous destination')
@@ -687,12 +791,46 @@ def scatter_rows_(dst: Tensor, index: Tensor, value: Tensor) -> None:
     feat = tuple(dst.shape[1:])
     val = torch.as_tensor(value, dtype=dst.dtype, device=dst.device)
     val = val.expand((idx.numel(),) + feat).contiguous()
-    if val.numel() == 0:
-        return
-    row_bytes = dst.element_size() * (dst[0].numel())
-    with _on(dst.device):
-        _lib.check(lib.rua_scatter_rows(val.data_ptr(), idx.data_ptr(), idx.numel(), row_bytes, dst.data_ptr(),
-                                        dst.shape[0], _stream()), 'rua_scatter_rows')
+    _scatter_rows_raw(dst, idx, val)
+    _bump_version(dst)
+
+
+class _ScatterRows(torch.autograd.Function):
+    """tracked ``dst[index] = value`` (core/set.py under autograd; ATen's IndexPutBackward0): the destination is modified
+    in place (mark_dirty), its gradient is the incoming one with the overwritten rows zeroed, the value's gradient is the
+    incoming rows gathered at ``index`` (summed over broadcast dimensions)."""
+
+    @staticmethod
+    def forward(ctx, dst: Tensor, index: Tensor, value: Tensor):
+        ctx.mark_dirty(dst)
+        idx = _i64(index).view(-1)
+        feat = tuple(dst.shape[1:])
+        ctx.value_shape = tuple(value.shape)
+        ctx.save_for_backward(idx)
+        val = value.detach().to(dtype=dst.dtype).expand((idx.numel(),) + feat).contiguous()
+        _scatter_rows_raw(dst, idx, val)
+        return dst
+
+    @staticmethod
+    def backward(ctx, grad: Tensor):
+        (idx,) = ctx.saved_tensors
+        g = grad.contiguous()
+        grad_value = grad_dst = None
+        if ctx.needs_input_grad[2]:
+            grad_value = _gather_rows_raw(g, idx).sum_to_size(ctx.value_shape) if idx.numel() else g.new_zeros(ctx.value_shape)
+        if ctx.needs_input_grad[0]:
+            grad_dst = g.clone()
+            if idx.numel():
+                _scatter_rows_raw(grad_dst, idx, g.new_zeros((1,) + tuple(g.shape[1:])).expand((idx.numel(),) + tuple(g.shape[1:])).contiguous())
+        return grad_dst, None, grad_value
+
+
+def scatter_rows_tracked_(dst: Tensor, index: Tensor, value) -> None:
+    require_cuda(dst, index)
+    if not dst.is_contiguous():
+        raise RuntimeError('torchrua_b200: in-place scatter needs a contiguous destination')
+    val = value if isinstance(value, Tensor) else torch.as_tensor(value, dtype=dst.dtype, device=dst.device)
+    _ScatterRows.apply(dst, index, val)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -908,7 +1046,7 @@ class _ScatterReduce(torch.autograd.Function):
         H = source[0].numel() if source.shape[0] else 0
         grad = torch.zeros_like(source)
         if K > 0 and H > 0:
-            ordered = _GatherRows.apply(source, srt)              # rows in sorted-index order
+            ordered = _gather_rows_raw(source, srt)               # rows in sorted-index order
             grad_ordered = torch.empty_like(ordered)
             dt = _DTYPES[source.dtype]
             with _on(source.device):

@@ -1,22 +1,25 @@
-"""Layout-aware in-place assignment -- mirror of torchrua/core/set.py (rua_scatter_rows moves the rows)."""
+"""Layout-aware in-place assignment -- mirror of torchrua/core/set.py.  rua_scatter_rows moves the rows; under
+autograd the same kernel runs inside an in-place autograd function (the reference's IndexPutBackward0)."""
 from typing import Tuple, Union
 
 import torch
 from torch import Tensor
 
 from torchrua_b200 import _native
-from torchrua_b200.core.get import _SEQ, _flat_key, _is_pair
+from torchrua_b200.core.get import _SEQ, _flat_key, _is_pair, _native_index
 from torchrua_b200.layout import C, L, P, R, T, Z
 
 Key = Union[int, Tensor, Tuple[Tensor, Tensor], Z]
 
 
 def _put(rows: Tensor, index: Tensor, value) -> None:
-    tracked = rows.requires_grad or (isinstance(value, Tensor) and value.requires_grad)
-    if rows.is_cuda and index.is_cuda and index.dtype in (torch.long, torch.int) and rows.is_contiguous() \
-            and not (tracked and torch.is_grad_enabled()):
-        _native.scatter_rows_(rows, index, value)
-    else:
+    if _native_index(rows, index) and rows.is_contiguous():
+        tracked = torch.is_grad_enabled() and (rows.requires_grad or (isinstance(value, Tensor) and value.requires_grad))
+        if tracked:
+            _native.scatter_rows_tracked_(rows, index, value)
+        else:
+            _native.scatter_rows_(rows, index, value)
+    else:   # boolean masks, CPU tensors, strided destinations: ATen's semantics and error messages
         super(T, rows).__setitem__(index, value)
 
 
@@ -35,6 +38,12 @@ def sequence_setitem(self: Z, key: Key, value: Tensor) -> None:
         _put(self.raw(), key.data, value)
         return None
     if _is_pair(key):
+        if isinstance(self, (L, R)) and not self.data.is_contiguous():
+            # raw() of a strided padded tensor is a COPY; the reference writes through self.data[b, col] (set.py:47,87)
+            b, t = key
+            col = t if isinstance(self, L) else self.size()[1] - self.token_sizes[b] + t
+            super(T, self.data).__setitem__((b, col), value)
+            return None
         _put(self.raw(), _flat_key(self, key), value)
         return None
     if isinstance(key, Tensor):

@@ -14,6 +14,9 @@ constexpr unsigned kFullMask = 0xffffffffu;
 extern int g_last_cuda_error;
 extern long long g_launch_count;
 
+// per-device counter of out-of-range explicit indices (index.cu); nullptr if it cannot be allocated
+unsigned long long* index_error_counter();
+
 inline int check_launch() {
   ++g_launch_count;
   cudaError_t e = cudaPeekAtLastError();

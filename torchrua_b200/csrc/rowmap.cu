@@ -37,6 +37,7 @@ struct RowMapParams {
   int32_t col_splits;      // gridDim.y
   const int64_t* gather_index;   // explicit source rows (rua_gather_rows) or NULL
   const int64_t* scatter_index;  // explicit destination rows (rua_scatter_rows) or NULL
+  unsigned long long* index_errors;   // device counter of out-of-range explicit indices (rows skipped / zero-filled)
   uint32_t div_wrv_m, div_wrv_s;  // narrow padded destinations: x / (width * row_vecs) for x < 2^31 (FastDiv)
   uint32_t div_rv_m, div_rv_s;    //                             x / row_vecs
 };
@@ -75,6 +76,18 @@ __device__ __forceinline__ int64_t simple_source_row(const RowMapParams& p, int6
 
 constexpr int64_t kPadRow = -1;
 constexpr int64_t kNoRow = -2;
+
+// explicit index tensors follow torch semantics: negative entries wrap around once.  An entry that is still out of
+// range is NOT dereferenced (ATen device-asserts there): gathers fill the row with zeros, scatters skip it, and
+// the per-device error counter is bumped (rua_index_error_count).
+__device__ __forceinline__ int64_t checked_index(const RowMapParams& p, int64_t v, int64_t bad) {
+  if (v < 0) v += p.s.rows;
+  if (v < 0 || v >= p.s.rows) {
+    if (p.index_errors) atomicAdd(p.index_errors, 1ull);
+    return bad;
+  }
+  return v;
+}
 
 __device__ __forceinline__ int64_t side_len(const rua_side_t& sd, int64_t base_len) {
   if (sd.len_xform == RUA_LEN_SAME) return base_len;
@@ -122,7 +135,12 @@ __device__ __forceinline__ int64_t map_row(const RowMapParams& p, int64_t j) {
     PackOff f{rg.poff, sh};
     int64_t steps = p.d.len_xform == RUA_LEN_CONST ? p.d.len_arg : rg.Tp - sh;
     td = owner_search(f, steps, j);
-    i = __ldg(rg.sorted + (j - f(td)));
+    // rank inside the time step.  A row beyond the step's batch size exists only when poff does not describe `rows`
+    // (the speculative C -> P launch of C.pack() whose cap turned out too small, or inconsistent metadata): treat it as
+    // padding instead of reading sorted[] out of bounds (the result of such a launch is discarded by the caller).
+    const int64_t base = f(td), r = j - base;
+    if (r >= f(td + 1) - base) return kPadRow;
+    i = __ldg(rg.sorted + r);
   } else {
     int64_t w = p.d.width;
     if (p.d.rows < (1ll << 31)) {
@@ -246,9 +264,11 @@ row_map_kernel(const RowMapParams p) {
   {
     int64_t j = j0 + lane;
     if (lane < rpw && j < rows) {
-      // explicit index tensors follow torch semantics: negative entries wrap around
-      if (p.gather_index) { srow = __ldg(p.gather_index + j); if (srow < 0) srow += p.s.rows; drow = j; }
-      else if (p.scatter_index) { srow = j; drow = __ldg(p.scatter_index + j); if (drow < 0) drow += p.s.rows; }
+      if (p.gather_index) { srow = checked_index(p, __ldg(p.gather_index + j), kPadRow); drow = j; }
+      else if (p.scatter_index) {
+        drow = checked_index(p, __ldg(p.scatter_index + j), kNoRow);
+        srow = drow == kNoRow ? kNoRow : j;
+      }
       else { srow = map_row(p, j); drow = j; }
       if (srow == kPadRow && p.pad_mode == RUA_PAD_ROW0) srow = 0;
     }
@@ -514,8 +534,11 @@ __device__ __forceinline__ void tile_body(const RowMapParams& p, OffFn f, int64_
       }
       const int64_t j = r0 + jr;
       int64_t i, td;
-      if (is_pack) { td = s; i = __ldg(p.rg.sorted + (j - base)); }
-      else { i = s; td = j - base; }
+      if (is_pack) {
+        td = s;
+        if (j - base >= f(s + 1) - base) { srow[r] = kPadRow; continue; }   // see map_row: rows poff does not describe
+        i = __ldg(p.rg.sorted + (j - base));
+      } else { i = s; td = j - base; }
       int64_t sr;
       if (SRC == kGenericSrc) {
         if (base_len < 0) base_len = __ldg(p.rg.off + i + 1) - __ldg(p.rg.off + i);
@@ -678,8 +701,12 @@ row_map_flat_kernel(const RowMapParams p) {
       col[r] = e - j * p.row_vecs;
       drow[r] = j;
       int64_t sr;
-      if (p.gather_index) { sr = __ldg(p.gather_index + j); if (sr < 0) sr += p.s.rows; }
-      else if (p.scatter_index) { sr = j; int64_t d = __ldg(p.scatter_index + j); drow[r] = d < 0 ? d + p.s.rows : d; }
+      if (p.gather_index) { sr = checked_index(p, __ldg(p.gather_index + j), kPadRow); }
+      else if (p.scatter_index) {
+        const int64_t d = checked_index(p, __ldg(p.scatter_index + j), kNoRow);
+        drow[r] = d;
+        sr = d == kNoRow ? kNoRow : j;
+      }
       else sr = map_row(p, j);
       if (sr == kPadRow && p.pad_mode == RUA_PAD_ROW0) sr = 0;
       srow[r] = sr;
@@ -1253,6 +1280,7 @@ static int index_rows(const void* src, const int64_t* gidx, const int64_t* sidx,
   p.s.rows = indexed_rows;  // size of the indexed side, for negative-index wrap-around
   p.gather_index = gidx;
   p.scatter_index = sidx;
+  p.index_errors = index_error_counter();
   p.pad_mode = RUA_PAD_FILL;
   return launch_row_map(p, row_bytes, n, (cudaStream_t)stream);
 }

@@ -15,8 +15,14 @@ i.e. 4 layout conversions (one rua_row_map launch each, plus their metadata kern
 reductions, every step recomputing all metadata (the per-tensor metadata cache is cleared each step).
 `value` = tokens through the whole step per second, summed over GPUs (weak scaling: per-GPU work fixed).
 
-Prints ONE JSON line (see the keys at the bottom).  `--impl reference` times the CPU restatement of the
-reference's path (oracle/rua_oracle.c, OpenMP over all host threads) on a bounded sample instead.
+Prints ONE JSON line (see the keys at the bottom).
+
+`--impl reference` times the UNMODIFIED reference (speedcell4/torchrua 0.5.1, staged under oracle/_ref by
+oracle/make_ref.py) through its own public API on the box's host cores -- the same step, the same seeds -- at the
+full configs[1] batch when that fits the time budget, else on the largest prefix of the batch that does (stated in
+`cpu_baseline.sample`).  The C + OpenMP port of the path (oracle/rua_oracle.c) is reported beside it as `cpu_port`.
+The repo arm additionally reports `reference_cuda`: the same reference driven on the SAME GPU (its stock ATen CUDA
+path, CUDA events) -- the kernel-to-beat of SURVEY.md 8d -- and per-op records for BASELINE configs 3, 4 and 5.
 """
 import argparse
 import json
@@ -42,6 +48,19 @@ def workload_lengths(world: int):
     import torch
     g = torch.Generator().manual_seed(0)
     return torch.randint(1, MAX_LEN + 1, (BATCH * world,), generator=g)
+
+
+STEP = 'C->P->L->R->C + segment_sum + segment_max'
+
+
+def make_config(world: int, exchange: str = 'peer'):
+    """the `config` object of BOTH arms (the driver compares them): what one step processes."""
+    glens = workload_lengths(world)
+    total = int(glens.sum())
+    return {'workload': WORKLOAD, 'step': STEP, 'batch_per_gpu': BATCH, 'tokens_total': total, 'hidden': HIDDEN,
+            'l2': 'inputs larger than L2: 2.17 GB per ragged layout, 4.29 GB per padded layout vs 126 MB',
+            'metadata': 'recomputed every step (cache cleared)',
+            'parallelism': f'sequence-sharded x{world}, length-balanced (snake), lengths exchange only'}
 
 
 # --------------------------------------------------------------------------------------------------
@@ -74,7 +93,7 @@ def time_cpu(steps: int, warmup: int, budget_s: float):
     from oracle import c_oracle as co
     co.build()
     co.use_all_cores()
-    n_seq = 512
+    n_seq = BATCH
     while True:
         step, n_tok, _ = cpu_pipeline_factory(n_seq)
         t0 = time.perf_counter()
@@ -166,26 +185,154 @@ class Clocks:
 
 
 # --------------------------------------------------------------------------------------------------
-# reference arm
+# reference arm: the UNMODIFIED reference (oracle/_ref) through its own public API
 # --------------------------------------------------------------------------------------------------
+REF_DIR = os.path.join(ROOT, 'oracle', '_ref')
+
+
+def import_reference():
+    """speedcell4/torchrua as staged by oracle/make_ref.py -- never the drop-in alias package at the repo root."""
+    if not os.path.exists(os.path.join(REF_DIR, 'torchrua', '__init__.py')):
+        return None
+    sys.path[:] = [p for p in sys.path if os.path.abspath(p or os.getcwd()) != ROOT]
+    sys.path.insert(0, REF_DIR)
+    import torchrua
+    assert os.path.dirname(os.path.dirname(os.path.abspath(torchrua.__file__))) == REF_DIR, torchrua.__file__
+    sys.path.insert(1, ROOT)
+    return torchrua
+
+
+def reference_pipeline_factory(ref, n_seq: int, device: str):
+    import torch
+    lens = workload_lengths(1)[:n_seq]
+    n = int(lens.sum())
+    g = torch.Generator().manual_seed(1)
+    data = torch.randn((n, HIDDEN), generator=g).to(torch.bfloat16).to(device)
+    lens = lens.to(device)
+
+    def step():
+        c = ref.C(data=data, token_sizes=lens)
+        back = c.pack().left(0).right(0).cat()
+        s = ref.segment_sum(back.data, back.token_sizes)
+        m = ref.segment_max(back.data, back.token_sizes)
+        return back, s, m
+
+    return step, n, data
+
+
+def time_reference_cpu(ref, steps: int, warmup: int, budget_s: float, n_seq: int = 0):
+    """-> (tokens_per_s, ms_per_step, n_seq, n_tokens, threads).  n_seq = 0: the full batch if the whole run fits the
+    budget (extrapolated from a 256-sequence probe: the reference is linear in tokens), else the largest power-of-two
+    prefix that does."""
+    import torch
+    threads = os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    if n_seq <= 0:
+        probe, n_probe, _ = reference_pipeline_factory(ref, 256, 'cpu')
+        probe()
+        t0 = time.perf_counter()
+        probe()
+        per_token = (time.perf_counter() - t0) / n_probe
+        n_seq = BATCH
+        total_tokens = int(workload_lengths(1).sum())
+        while n_seq > 64 and per_token * total_tokens * (n_seq / BATCH) * (steps + warmup) > budget_s:
+            n_seq //= 2
+    step, n_tok, data = reference_pipeline_factory(ref, n_seq, 'cpu')
+    for _ in range(warmup):
+        out = step()
+    if warmup:
+        assert torch.equal(out[0].data, data), 'reference round trip is not the identity'
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        step()
+    dt = time.perf_counter() - t0
+    return n_tok * steps / dt, dt / steps * 1e3, n_seq, n_tok, threads
+
+
+def time_reference_cuda(ref, steps: int, warmup: int, n_seq: int):
+    """the reference's stock ATen CUDA path on the same GPU, CUDA events around `steps` steps."""
+    import torch
+    torch.cuda.set_device(0)
+    step, n_tok, data = reference_pipeline_factory(ref, n_seq or BATCH, 'cuda')
+    for _ in range(max(warmup, 1)):
+        out = step()
+    torch.cuda.synchronize()
+    assert torch.equal(out[0].data, data), 'reference round trip is not the identity'
+    del out
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(steps):
+        step()
+    b.record()
+    torch.cuda.synchronize()
+    ms = a.elapsed_time(b) / steps
+    return n_tok / (ms * 1e-3), ms, n_seq or BATCH, n_tok
+
+
 def run_reference(args):
     rank = int(os.environ.get('RANK', '0'))
     if rank != 0:
         return
-    tps, ms, n_seq, n_tok, threads = time_cpu(args.steps, max(args.warmup, 1), budget_s=150.0)
-    sample = f'first {n_seq} of the {BATCH} sequences ({n_tok} tokens, hidden {HIDDEN} bf16) per step'
+    ref = import_reference()
+    port = None
+    if args.ref_device == 'cuda':
+        assert ref is not None, 'oracle/_ref is not staged'
+        tps, ms, n_seq, n_tok = time_reference_cuda(ref, args.steps, args.warmup, args.ref_seqs)
+        kind, threads, device = 'reference', 0, 'the same GPU (stock ATen CUDA kernels), CUDA events'
+    elif ref is not None:
+        tps, ms, n_seq, n_tok, threads = time_reference_cpu(ref, args.steps, max(args.warmup, 1), args.ref_budget,
+                                                            args.ref_seqs)
+        kind, device = 'reference', 'host CPU (no GPU work)'
+    else:   # the staged reference did not travel: fall back to the C port of the same path, and say so
+        tps, ms, n_seq, n_tok, threads = time_cpu(args.steps, max(args.warmup, 1), budget_s=150.0)
+        kind, device = 'port', 'host CPU (no GPU work)'
+    if ref is not None and args.ref_device == 'cpu' and not args.no_port:
+        try:
+            ptps, pms, pseq, ptok, pthreads = time_cpu(steps=3, warmup=1, budget_s=30.0)
+            port = {'value': ptps, 'unit': 'tokens/s', 'cores': pthreads, 'kind': 'port', 'ms_per_step': pms,
+                    'sample': sample_text(pseq, ptok),
+                    'what': 'oracle/rua_oracle.c: C + OpenMP restatement of the same path, all host threads'}
+        except Exception as e:   # the port is a second opinion, never the headline
+            port = {'unavailable': f'{type(e).__name__}: {e}'}
+    what = ('UNMODIFIED speedcell4/torchrua 0.5.1 (oracle/_ref) through its public API: C(...).pack().left(0).right(0).cat(), '
+            'segment_sum, segment_max' if kind == 'reference' else
+            'oracle/rua_oracle.c: C restatement of the reference path, OpenMP over all host threads (oracle/_ref missing)')
     line = {
         'impl': 'reference', 'metric': METRIC, 'value': tps, 'unit': 'tokens/s', 'n_gpus': args.gpus,
         'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms, 'higher_is_better': True, 'scaling': 'weak',
         'vs_baseline': None, 'dtype': 'bf16', 'data': 'synthetic',
-        'config': {'workload': WORKLOAD, 'step': 'C->P->L->R->C + segment_sum + segment_max',
-                   'device': 'host CPU (no GPU work)', 'sample': sample},
-        'cpu_baseline': {'value': tps, 'unit': 'tokens/s', 'cores': threads, 'kind': 'port', 'sample': sample,
-                         'what': 'oracle/rua_oracle.c: C restatement of the reference path, OpenMP over all host threads'},
+        'config': make_config(args.gpus),
+        'device': device,
+        'cpu_baseline': {'value': tps, 'unit': 'tokens/s', 'cores': threads, 'kind': kind, 'ms_per_step': ms,
+                         'sample': sample_text(n_seq, n_tok), 'full_batch': n_seq == BATCH, 'what': what},
+        'cpu_port': port,
         'e2e': {'value': tps, 'unit': 'tokens/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
         'gpu_launches': 0,
     }
     emit(line)
+
+
+def sample_text(n_seq: int, n_tok: int) -> str:
+    if n_seq == BATCH:
+        return f'the full batch: all {BATCH} sequences ({n_tok} tokens, hidden {HIDDEN} bf16) per step'
+    return f'first {n_seq} of the {BATCH} sequences ({n_tok} tokens, hidden {HIDDEN} bf16) per step'
+
+
+def reference_subprocess(extra, timeout_s: float):
+    """run `bench.py --impl reference ...` in a fresh interpreter (the reference and the package under test both
+    patch torch.Tensor / PackedSequence process-wide and cannot share one) and parse its JSON line."""
+    env = dict(os.environ)
+    for k in ('RANK', 'WORLD_SIZE', 'LOCAL_RANK', 'MASTER_ADDR', 'MASTER_PORT'):
+        env.pop(k, None)
+    try:
+        out = subprocess.run([sys.executable, os.path.join(ROOT, 'bench.py'), '--impl', 'reference', '--no-port'] + extra,
+                             stdout=subprocess.PIPE, stderr=subprocess.PIPE, env=env, timeout=timeout_s, cwd=ROOT)
+        lines = [ln for ln in out.stdout.decode().splitlines() if ln.startswith('{')]
+        if out.returncode != 0 or not lines:
+            return {'unavailable': f'rc {out.returncode}: {out.stderr.decode()[-300:]}'}
+        return json.loads(lines[-1])
+    except Exception as e:
+        return {'unavailable': f'{type(e).__name__}: {e}'}
 
 
 # --------------------------------------------------------------------------------------------------
@@ -318,16 +465,19 @@ def run_ours(args):
         pass
     peak = float(peaks.get('hbm_gbs', 6650.0))
     peak_src = 'measured (MEASURED_PEAKS.json hbm_gbs)' if 'hbm_gbs' in peaks else 'fallback 6.65 TB/s (B200_PROFILING.md)'
-    traffic = None
+    # dram__bytes_read.sum + dram__bytes_write.sum per launch of the same kernel from the committed `ncu --set full`
+    # capture of this command (profiles/roofline_traffic.json names the capture it came from); never measured live
+    traffic = traffic_src = None
     try:
-        traffic = json.load(open(os.path.join(ROOT, 'profiles', 'roofline_traffic.json'))).get('row_map_bytes_per_launch')
+        tr = json.load(open(os.path.join(ROOT, 'profiles', 'roofline_traffic.json')))
+        traffic, traffic_src = tr.get('row_map_bytes_per_launch'), tr.get('source')
     except Exception:
         pass
     rm = per.get('row_map', [1.0, 0, 1])
     achieved = rm[1] / (rm[0] * 1e-3) / 1e9
-    roofline = {'bound': 'hbm', 'kernel': 'row_map_kernel<uint4> (4 launches per step: C->P, P->L, L->R, R->C)',
+    roofline = {'bound': 'hbm', 'kernel': 'row_map_kernel<V256> (256-bit vectors; 4 launches per step: C->P, P->L, L->R, R->C)',
                 'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak, 'traffic': traffic,
-                'peak_source': peak_src, 'frac_of_nameplate_8000': achieved / 8000.0,
+                'traffic_source': traffic_src, 'peak_source': peak_src, 'frac_of_nameplate_8000': achieved / 8000.0,
                 'algorithmic_bytes_per_launch': rm[1] / max(rm[2], 1), 'avg_launch_ms': rm[0] / max(rm[2], 1),
                 'share_of_step': rm[0] / ms_total}
     sr = per.get('segment_reduce')
@@ -405,25 +555,56 @@ def run_ours(args):
         gather = time_output_gather(args, step, data, lens, lens_host, glens, parts, rank, world, dev, total_tokens,
                                     barrier)
 
-    # ---- CPU baseline (rank 0, single-GPU run only) ------------------------------------------------
-    cpu = None
+    # ---- BASELINE configs 3 / 5 (one GPU) and 4 (any N): per-op records, driver-visible ------------------
+    del h_data, h_back, h_sum, h_max, d_in
+    torch.cuda.empty_cache()
+    configs = {}
+    if not args.no_configs:
+        from benchmarks import cfg4 as cfg4_bench
+        configs['cfg4'] = cfg4_bench.run(rank, world, dev, micro_batches=args.cfg4_micro_batches)
+        if world == 1:
+            from benchmarks import ops as ops_bench
+            for key, fn in (('cfg3', ops_bench.cfg3), ('cfg5', ops_bench.cfg5)):
+                rows = []
+                fn(rows, reps=5, quiet=True)
+                configs[key] = ops_bench.compact(rows)
+                torch.cuda.empty_cache()
+
+    # ---- the reference on the SAME GPU and on the host cores (rank 0, single-GPU run only) -----------------
+    cpu = ref_cuda = port = None
     if rank == 0 and world == 1 and not args.no_cpu:
+        torch.cuda.synchronize()
+        r = reference_subprocess(['--ref-device', 'cuda', '--steps', '5', '--warmup', '5'], timeout_s=300)
+        if 'unavailable' in r:
+            ref_cuda = r
+        else:
+            ref_cuda = {'value': r['value'], 'unit': 'tokens/s', 'ms_per_step': r['ms_per_step'],
+                        'sample': r['cpu_baseline']['sample'], 'steps': 5, 'warmup': 5,
+                        'what': 'the UNMODIFIED reference (oracle/_ref) running the same step on the same B200 through '
+                                'its stock ATen CUDA path, CUDA events, separate process',
+                        'speedup_of_value': value / r['value']}
+        r = reference_subprocess(['--steps', '3', '--warmup', '1', '--ref-seqs', '512'], timeout_s=300)
+        if 'unavailable' in r:
+            cpu = None
+        else:
+            cpu = dict(r['cpu_baseline'])
+            cpu['sample'] += ', 3 steps'
         tps, cms, n_seq, cn, threads = time_cpu(steps=3, warmup=1, budget_s=25.0)
-        cpu = {'value': tps, 'unit': 'tokens/s', 'cores': threads, 'kind': 'port', 'ms_per_step': cms,
-               'sample': f'first {n_seq} of the {BATCH} sequences ({cn} tokens, hidden {HIDDEN} bf16), 3 steps',
-               'what': 'oracle/rua_oracle.c (C restatement of the reference path, OpenMP, all host threads)'}
+        port = {'value': tps, 'unit': 'tokens/s', 'cores': threads, 'kind': 'port', 'ms_per_step': cms,
+                'sample': sample_text(n_seq, cn) + ', 3 steps',
+                'what': 'oracle/rua_oracle.c (C + OpenMP restatement of the reference path, all host threads)'}
+        if cpu is None:
+            cpu = port
 
     if rank == 0:
         line = {
             'metric': METRIC, 'value': value, 'unit': 'tokens/s', 'n_gpus': world, 'steps': args.steps,
             'warmup': max(args.warmup, 3), 'ms_per_step': ms_total / args.steps, 'higher_is_better': True,
             'scaling': 'weak', 'vs_baseline': None, 'dtype': 'bf16', 'data': 'synthetic',
-            'config': {'workload': WORKLOAD, 'step': 'C->P->L->R->C + segment_sum + segment_max',
-                       'batch_per_gpu': BATCH, 'tokens_per_gpu': n_tok, 'tokens_total': total_tokens, 'hidden': HIDDEN,
-                       'l2': 'inputs larger than L2: 2.17 GB per ragged layout, 4.29 GB per padded layout vs 126 MB',
-                       'metadata': 'recomputed every step (cache cleared)',
-                       'parallelism': f'sequence-sharded x{world}, length-balanced (snake), lengths exchange only ({args.exchange if world > 1 else "none"})'},
-            'roofline': roofline, 'kernels': kernels, 'cpu_baseline': cpu,
+            'config': make_config(world),
+            'exchange': args.exchange if world > 1 else 'none', 'tokens_per_gpu': n_tok,
+            'roofline': roofline, 'kernels': kernels, 'cpu_baseline': cpu, 'cpu_port': port,
+            'reference_cuda': ref_cuda, 'configs': configs,
             'e2e': {'value': e2e_value, 'unit': 'tokens/s', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h,
                     'steps': e2e_steps, 'ms_per_step': float(ems) / e2e_steps,
                     'what': 'every step: pinned host C batch -> H2D -> same step through the public API -> D2H of the '
@@ -539,7 +720,15 @@ def main():
     ap.add_argument('--steps', type=int, default=20)
     ap.add_argument('--warmup', type=int, default=5)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
-    ap.add_argument('--no-cpu', action='store_true', help='skip the cpu_baseline leg')
+    ap.add_argument('--no-cpu', action='store_true', help='skip the cpu_baseline / reference_cuda legs')
+    ap.add_argument('--no-configs', action='store_true', help='skip the configs[2..4] records')
+    ap.add_argument('--no-port', action='store_true', help='reference arm: skip the C port beside the reference')
+    ap.add_argument('--cfg4-micro-batches', type=int, default=0,
+                    help='configs[3] record: micro-batches per rank to time (0 = the whole 64 M-token job)')
+    ap.add_argument('--ref-device', default='cpu', choices=['cpu', 'cuda'],
+                    help='reference arm: host cores (the contract arm) or the same GPU (the reference_cuda record)')
+    ap.add_argument('--ref-seqs', type=int, default=0, help='reference arm: sequences per step (0 = full batch if it fits the budget)')
+    ap.add_argument('--ref-budget', type=float, default=200.0, help='reference arm: seconds for the whole run')
     ap.add_argument('--no-gather', action='store_true', help='skip the output-gather legs of multi-GPU runs')
     ap.add_argument('--exchange', default='peer', choices=['peer', 'nccl', 'none'],
                     help='per-step lengths exchange of multi-GPU runs: peer-window stores (default), NCCL all-gather, or none (diagnostic)')

@@ -26,14 +26,17 @@ import torchrua_b200 as rua  # noqa: E402
 from torchrua_b200 import _native, shard  # noqa: E402
 
 TOKENS, HIDDEN, MAX_LEN, MICRO_TOKENS = 64_000_000, 2048, 512, 2_000_000
+PEAK = 6526.2
+try:
+    PEAK = float(json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json')))['hbm_gbs'])
+except Exception:
+    pass
 
 
-def main():
-    rank, world, local = (int(os.environ.get(k, d)) for k, d in (('RANK', 0), ('WORLD_SIZE', 1), ('LOCAL_RANK', 0)))
-    torch.cuda.set_device(local)
-    dev = torch.device('cuda', local)
-    dist.init_process_group('nccl' if world > 1 else 'gloo', device_id=dev if world > 1 else None,
-                            **({} if 'MASTER_ADDR' in os.environ else {'init_method': 'tcp://127.0.0.1:29555', 'rank': 0, 'world_size': 1}))
+def run(rank: int, world: int, dev, micro_batches: int = 0):
+    """the whole 64 M-token job on `world` ranks (STRONG scaling: the total is fixed, each rank walks 1/world of it in
+    2 M-token micro-batches).  Needs an initialised NCCL process group when world > 1.  Returns the record (identical on
+    every rank).  `micro_batches` > 0 times only that many micro-batches per rank (smoke runs)."""
     g = torch.Generator().manual_seed(0)
     b_total = int(TOKENS / ((1 + MAX_LEN) / 2))
     glens = torch.randint(1, MAX_LEN + 1, (b_total,), generator=g)
@@ -50,13 +53,15 @@ def main():
         end = max(end, start + 1)
         cuts.append((start, end))
         start = end
+    if micro_batches > 0:
+        cuts = cuts[:micro_batches]
     row = HIDDEN * 2
     windows = shard.PeerWindows(2 * ((b_total * row + 255) // 256 * 256)) if world > 1 else None
     max_off = (b_total * row + 255) // 256 * 256
-    sums_local = torch.empty((lens_host.numel(), HIDDEN), dtype=torch.bfloat16, device=dev)
-    maxs_local = torch.empty_like(sums_local)
+    sums_local = torch.zeros((lens_host.numel(), HIDDEN), dtype=torch.bfloat16, device=dev)
+    maxs_local = torch.zeros_like(sums_local)
 
-    ms_total, checked, alg_bytes = 0.0, 0, 0
+    ms_total, checked, alg_bytes, tokens_done = 0.0, 0, 0, 0
     gen = torch.Generator(device=dev).manual_seed(1 + rank)
     # the first micro-batch runs twice: once untimed (allocator growth, lazy kernel loading), then for the record
     for k, (a, b) in enumerate([cuts[0]] + cuts):
@@ -79,6 +84,7 @@ def main():
         if k == 0:
             continue
         ms_total += e0.elapsed_time(e1)
+        tokens_done += n
         # algorithmic bytes: C->P, P->C, L->C: 2 N D each; C->L: N D + B T D; each reduction: N D + B D
         padded = (b - a) * int(lens_host[a:b].max()) * row
         alg_bytes += 6 * n * row + (n * row + padded) + 2 * (n * row + (b - a) * row)
@@ -109,27 +115,48 @@ def main():
     gather_ms = g0.elapsed_time(g1)
     assert torch.equal(gs[mine.to(dev)], sums_local) and torch.equal(gm[mine.to(dev)], maxs_local)
     chk = torch.stack([gs.view(torch.int16).long().sum(), gm.view(torch.int16).long().sum()])
-    t = torch.tensor([ms_total, gather_ms], dtype=torch.double, device=dev)
+    t = torch.tensor([ms_total, gather_ms, float(tokens_done)], dtype=torch.double, device=dev)
+    tok = torch.tensor([float(tokens_done)], dtype=torch.double, device=dev)
     if world > 1:
         lo, hi = chk.clone(), chk.clone()
         dist.all_reduce(lo, op=dist.ReduceOp.MIN)
         dist.all_reduce(hi, op=dist.ReduceOp.MAX)
         assert torch.equal(lo, hi), 'ranks disagree on the gathered results'
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    if rank == 0:
-        pipe_ms, gather_ms = float(t[0]), float(t[1])
-        print(json.dumps({
-            'workload': 'configs[3]: C->P->C + C->L->C + segment_sum + segment_max, 64M tokens, hidden 2048 bf16, sequence-sharded',
-            'n_gpus': world, 'tokens_total': total, 'sequences_total': b_total, 'micro_batches_per_rank': len(cuts), 'warmup': 'first micro-batch run once untimed',
-            'micro_batch_tokens': MICRO_TOKENS, 'imbalance': shard.partition_imbalance(glens, parts),
-            'pipeline_ms_max_over_ranks': pipe_ms, 'gather_ms': gather_ms,
-            'tokens_per_s': total / (pipe_ms * 1e-3), 'tokens_per_s_with_gather': total / ((pipe_ms + gather_ms) * 1e-3),
-            'algorithmic_GBs_per_gpu': alg_bytes / (pipe_ms * 1e-3) / 1e9,
-            'checks': {'round_trips_identity': True, 'reductions_sampled': checked, 'gathered_tables_identical': True},
-        }))
+        dist.all_reduce(tok, op=dist.ReduceOp.SUM)
+    pipe_ms, gather_ms, done = float(t[0]), float(t[1]), float(tok[0])
+    whole = micro_batches <= 0
+    record = {
+        'workload': 'configs[3]: C->P->C + C->L->C + segment_sum + segment_max, 64M tokens, hidden 2048 bf16, sequence-sharded, '
+                    'length-balanced; per-sequence results of ALL sequences gathered on every rank',
+        'scaling': 'strong', 'n_gpus': world, 'tokens_total': total, 'tokens_timed': int(done), 'whole_job': whole,
+        'sequences_total': b_total, 'micro_batches_per_rank': len(cuts), 'warmup': 'first micro-batch run once untimed',
+        'micro_batch_tokens': MICRO_TOKENS, 'imbalance': shard.partition_imbalance(glens, parts),
+        'pipeline_ms_max_over_ranks': pipe_ms, 'gather_ms': gather_ms,
+        'tokens_per_s': done / (pipe_ms * 1e-3), 'tokens_per_s_with_gather': done / ((pipe_ms + gather_ms) * 1e-3),
+        'algorithmic_GBs_per_gpu': alg_bytes / (ms_total * 1e-3) / 1e9,
+        'frac_of_measured_peak_per_gpu': alg_bytes / (ms_total * 1e-3) / 1e9 / PEAK,
+        'timing': 'CUDA events around every micro-batch (data generation excluded), summed; max over ranks',
+        'checks': {'round_trips_identity': True, 'reductions_sampled': checked, 'gathered_tables_identical': True},
+    }
     if windows is not None:
         windows.close()
-    dist.destroy_process_group()
+    del sums_local, maxs_local, gs, gm
+    torch.cuda.empty_cache()
+    return record
+
+
+def main():
+    rank, world, local = (int(os.environ.get(k, d)) for k, d in (('RANK', 0), ('WORLD_SIZE', 1), ('LOCAL_RANK', 0)))
+    torch.cuda.set_device(local)
+    dev = torch.device('cuda', local)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=dev)
+    record = run(rank, world, dev)
+    if rank == 0:
+        print(json.dumps(record))
+    if world > 1:
+        dist.destroy_process_group()
 
 
 if __name__ == '__main__':

@@ -53,6 +53,25 @@ def timed(fn, reps, clear=True):
     return statistics.median(api), statistics.median(ker)
 
 
+QUIET = False
+
+
+def compact(rows):
+    """the per-op record bench.py embeds in its JSON line: algorithmic bytes, event-timed ms (public API call with the
+    metadata cache cleared / kernel launches only) and the fraction of the measured HBM peak for both."""
+    out = []
+    for r in rows:
+        e = {'op': r['op'], 'alg_bytes': int(r['alg_GB'] * 1e9), 'api_ms': round(r['api_ms'], 4),
+             'api_frac': round(r['api_frac_of_measured_peak'], 4)}
+        if r.get('kernel_GBs'):
+            e['kernel_ms'] = round(r['kernel_ms'], 4)
+            e['kernel_frac'] = round(r['kernel_frac_of_measured_peak'], 4)
+        if 'aten_payload_ms' in r:
+            e['aten_payload_ms'] = round(r['aten_payload_ms'], 4)
+        out.append(e)
+    return out
+
+
 def row(results, cfg, name, nbytes, tokens, fn, reps, aten=None):
     api_ms, ker_ms = timed(fn, reps)
     r = {'cfg': cfg, 'op': name, 'api_ms': api_ms, 'kernel_ms': ker_ms, 'alg_GB': nbytes / 1e9,
@@ -65,6 +84,8 @@ def row(results, cfg, name, nbytes, tokens, fn, reps, aten=None):
         r['aten_payload_ms'] = aten_ms
         r['speedup_vs_aten_payload'] = aten_ms / api_ms
     results.append(r)
+    if QUIET:
+        return
     k = f"{r['kernel_GBs']:7.0f}" if r['kernel_GBs'] else '      -'
     extra = f"  aten {r['aten_payload_ms']:8.3f} ms (x{r['speedup_vs_aten_payload']:.1f})" if aten is not None else ''
     print(f"cfg{cfg} {name:28s} api {api_ms:8.3f} ms {r['api_GBs']:7.0f} GB/s | kernel {k} GB/s "
@@ -72,7 +93,9 @@ def row(results, cfg, name, nbytes, tokens, fn, reps, aten=None):
           flush=True)
 
 
-def cfg2(results, reps):
+def cfg2(results, reps, quiet=False):
+    global QUIET
+    QUIET = quiet
     g = torch.Generator().manual_seed(0)
     lens = torch.randint(1, 513, (4096,), generator=g)
     n, b, t, d = int(lens.sum()), 4096, int(lens.max()), 2048
@@ -155,7 +178,7 @@ def cfg2(results, reps):
 
     cl = rua.C(data=leaf, token_sizes=lc)
     bwd(lambda: cl.pack().data, 2 * nd, 'bwd C->P')
-    bwd(lambda: cl.left(0).data, nd + btd, 'bwd C->L')
+    bwd(lambda: cl.left(0).data, 2 * nd + 8 * b, 'bwd C->L')   # reads the N live rows of the padded gradient, writes N rows
     bwd(lambda: rua.segment_sum(leaf, lc), nd + b * d, 'bwd segment_sum',
         lambda: torch.segment_reduce(leaf, 'sum', lengths=lc, unsafe=True))
     bwd(lambda: rua.segment_max(leaf, lc), 3 * nd + 2 * b * d, 'bwd segment_max',
@@ -163,11 +186,14 @@ def cfg2(results, reps):
     bwd(lambda: rua.segment_logsumexp(leaf, lc), 2 * nd + 2 * b * d, 'bwd segment_logsumexp')
 
 
-def cfg3(results, reps):
+def cfg3(results, reps, quiet=False):
+    global QUIET
+    QUIET = quiet
     rng = np.random.default_rng(0)
     sizes = np.minimum(rng.zipf(1.5, 16384), 4096).astype(np.int64)
     n, s, d = int(sizes.sum()), 16384, 8192
-    print(f'cfg3: B={s}, Zipf(a=1.5) clipped to 4096, N={n}, hidden 4096 bf16, payload {n * d / 1e9:.2f} GB', flush=True)
+    if not quiet:
+        print(f'cfg3: B={s}, Zipf(a=1.5) clipped to 4096, N={n}, hidden 4096 bf16, payload {n * d / 1e9:.2f} GB', flush=True)
     data = torch.randn((n, 4096), device='cuda', dtype=torch.bfloat16)
     sz = torch.from_numpy(sizes).cuda()
     nd = n * d
@@ -186,7 +212,9 @@ def cfg3(results, reps):
     row(results, 3, 'P->C', 2 * nd, n, lambda: p.cat(), reps)
 
 
-def cfg5(results, reps):
+def cfg5(results, reps, quiet=False):
+    global QUIET
+    QUIET = quiet
     g = torch.Generator().manual_seed(0)
     lens = torch.randint(1, 65, (1_000_000,), generator=g)
     n, b, t = int(lens.sum()), 1_000_000, 64

@@ -294,7 +294,9 @@ def seg(rua, dev, seed, B, lo, hi, feat, dtype, fns=('sum', 'mean', 'max', 'min'
         for dk in KINDS:
             dd = build(dk, d)
             for fn in fns:
-                out[f'{sk}.seg({dk}, {fn})'] = plain(s.seg(dd, getattr(rua, 'segment_' + fn)))
+                # the result takes the layout of the DURATIONS' owner; a P result is ordered by the number of
+                # durations per sequence, which ties -> canonical form
+                out[f'{sk}.seg({dk}, {fn})'] = emit(s.seg(dd, getattr(rua, 'segment_' + fn)), False)
     return out
 
 

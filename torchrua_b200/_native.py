@@ -183,15 +183,11 @@ class Ragged:
     Tp: int = 0
     _keep: list = field(default_factory=list)
     _spec_ok: bool = False            # the speculative early launch of _ensure_pack_fused held
-    _event: Optional[torch.cuda.Event] = None   # recorded after the producer kernels, on _stream (see _cache_get)
-    _stream: int = 0
+    _stream: Optional[int] = None     # the stream the producer kernels were enqueued on (see _cache_get)
 
     def mark_ready(self):
         with _on(self.device):
-            st = torch.cuda.current_stream()
-            self._stream = st.cuda_stream
-            self._event = torch.cuda.Event()
-            self._event.record(st)
+            self._stream = _stream()
 
     def _sync_stats(self):
         # the one inherent D2H: output shapes depend on device data (16 bytes, pinned, stream-ordered)
@@ -295,17 +291,19 @@ def _cache_get(key_tensor: Tensor, tag: str):
     counter (another framework, a C extension) do not -- call ``clear_metadata_cache()`` after those.
 
     The cached device arrays were produced on the stream that was current when the entry was built; a consumer on
-    ANOTHER stream waits for the event recorded there before it launches anything that reads them."""
+    ANOTHER stream first waits for that stream (everything enqueued there so far: a superset of the producer
+    kernels -- recording an event per entry would tax the common single-stream case by ~10 us per call)."""
     ent = _CACHE.get((id(key_tensor), tag))
     if ent is None:
         return None
     ref, version, value = ent
     if ref() is key_tensor and key_tensor._version == version:
-        ev = getattr(value, '_event', None)
-        if ev is not None:
+        made_on = getattr(value, '_stream', None)
+        if made_on is not None:
             cur = torch.cuda.current_stream(value.device)
-            if cur.cuda_stream != value._stream:
-                cur.wait_event(ev)
+            if cur.cuda_stream != made_on:
+                cur.wait_stream(torch.cuda.ExternalStream(made_on, device=value.device) if made_on else
+                                torch.cuda.default_stream(value.device))
         return value
     del _CACHE[(id(key_tensor), tag)]
     return None

@@ -188,6 +188,84 @@ emit_ptr_kernel(const int64_t* __restrict__ off, int64_t S, int64_t n, const int
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// ptr / idx emit with MANY SHORT segments (C.ptr / L.idx / R.idx / major_sizes_to_ptr at BASELINE config 5: 1 M
+// sequences of 1..64 tokens).  The tile kernel above pays a serial chain per CTA (two searches -> staged offsets ->
+// block scan -> emit, three barriers; ncu: 6 of 8 warps idle at the first barrier, 45 % DRAM).  Here a WARP owns 32
+// consecutive segments, i.e. one contiguous range of output positions:
+//   * lane i reads off[s0 + i], off[s0 + i + 1] (coalesced; no search, no block barrier);
+//   * every lane paints ITS OWN lane number over its segment's positions in a 2 KB byte window of shared memory (all
+//     lanes busy; a window lying inside one long segment is not painted at all);
+//   * the warp then walks the window four positions per lane: one LDS.32 yields the four owners, shuffles fetch the
+//     owners' segment starts, and each output array gets one 256-bit store per lane (a full sector).
+// ------------------------------------------------------------------------------------------------
+constexpr int kEwThreads = 256;
+constexpr int kEwWarps = kEwThreads / 32;
+constexpr int kEwWin = 2048;   // positions per window
+
+__global__ void __launch_bounds__(kEwThreads)
+emit_ptr_warpseg_kernel(const int64_t* __restrict__ off, int64_t S, int64_t n, int64_t* __restrict__ which,
+                        int64_t* __restrict__ within, int64_t* __restrict__ flat, int64_t stride, int right_align,
+                        int wide_stores) {
+  __shared__ __align__(16) unsigned char s_own[kEwWarps][kEwWin];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int64_t s0 = ((int64_t)blockIdx.x * kEwWarps + warp) * 32;
+  if (s0 >= S) return;                                   // warp-uniform; no block-level synchronisation below
+  const int64_t s = s0 + lane;
+  int64_t beg = s < S ? __ldg(off + s) : n, end = s < S ? __ldg(off + s + 1) : n;
+  const int64_t shift = right_align ? stride - (end - beg) : 0;   // R.idx: tokens sit at the end of their padded row
+  beg = beg < n ? beg : n;
+  end = end < n ? end : n;
+  const int64_t wbeg = shfl_i64(beg, 0), wend = shfl_i64(end, 31);
+  unsigned char* own = s_own[warp];
+  for (int64_t w0 = wbeg & ~(int64_t)3; w0 < wend; w0 += kEwWin) {
+    const int64_t w1 = w0 + kEwWin < wend ? w0 + kEwWin : wend;
+    const unsigned who = __ballot_sync(kFullMask, beg <= w0 && end >= w0 + kEwWin);
+    if (!who) {
+      const int lo = (int)((beg > w0 ? beg : w0) - w0), hi = (int)((end < w1 ? end : w1) - w0);
+      for (int p = lo; p < hi; ++p) own[p] = (unsigned char)lane;
+    }
+    __syncwarp();
+    const int groups = (int)((w1 - w0 + 3) >> 2);        // groups of 4 positions in this window (warp-uniform)
+    for (int g0 = 0; g0 < groups; g0 += 32) {
+      const int g = g0 + lane;
+      int o[4];
+      if (who) {
+        o[0] = o[1] = o[2] = o[3] = __ffs(who) - 1;
+      } else {
+        const uchar4 b = reinterpret_cast<const uchar4*>(own)[g < groups ? g : 0];
+        o[0] = b.x & 31; o[1] = b.y & 31; o[2] = b.z & 31; o[3] = b.w & 31;   // unpainted bytes: any lane, never stored
+      }
+      const int64_t p0 = w0 + 4 * (int64_t)g;
+      int64_t sv[4], wv[4], fv[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int64_t ob = shfl_i64(beg, o[e]);
+        sv[e] = s0 + o[e];
+        wv[e] = p0 + e - ob;
+        if (flat) fv[e] = sv[e] * stride + wv[e] + shfl_i64(shift, o[e]);
+      }
+      if (g >= groups) continue;
+      if (wide_stores && p0 >= wbeg && p0 + 4 <= w1) {
+        if (which) st_v4_i64(which + p0, sv);
+        if (within) st_v4_i64(within + p0, wv);
+        if (flat) st_v4_i64(flat + p0, fv);
+      } else {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const int64_t p = p0 + e;
+          if (p >= wbeg && p < w1) {
+            if (which) which[p] = sv[e];
+            if (within) within[p] = wv[e];
+            if (flat) flat[p] = fv[e];
+          }
+        }
+      }
+    }
+    __syncwarp();
+  }
+}
+
 }  // namespace rua
 
 using namespace rua;
@@ -225,6 +303,16 @@ int rua_emit_ptr(const int64_t* off, int64_t S, int64_t n, const int64_t* relabe
   const int64_t blocks = ceil_div(n, kEmitTile);
   if (blocks >= (1ll << 31)) return RUA_ERR_UNSUPPORTED;
   const uintptr_t align = (uintptr_t)which | (uintptr_t)within | (uintptr_t)flat;
+  // many short segments (C.ptr / L.idx / R.idx of a large batch): a warp per 32 segments, no per-tile decode chain
+  static const int64_t ws_min = [] { const char* e = getenv("RUA_WARPSEG_MIN_S"); return e ? atoll(e) : 32768ll; }();
+  if (!relabel && S >= ws_min && n <= 256 * S) {
+    const int64_t wblocks = ceil_div(S, (int64_t)kEwWarps * 32);
+    if (wblocks >= (1ll << 31)) return RUA_ERR_UNSUPPORTED;
+    emit_ptr_warpseg_kernel<<<(unsigned)wblocks, kEwThreads, 0, (cudaStream_t)stream>>>(off, S, n, which, within, flat,
+                                                                                       stride, right_align,
+                                                                                       (align & 31u) == 0);
+    return check_launch();
+  }
   emit_ptr_kernel<<<(unsigned)blocks, kEmitThreads, 0, (cudaStream_t)stream>>>(off, S, n, relabel, which, within,
                                                                             flat, stride, right_align,
                                                                             (align & 31u) == 0);

@@ -29,6 +29,10 @@ int flat_rows_per_tile(int32_t dtype, int64_t H);
 int flat_launch(int32_t dtype, int64_t H, int32_t op, const void* data, const int64_t* ridx, const int64_t* off,
                 int64_t N, int64_t S, void* out, void* head, void* tail, int64_t* tail_seg, void* hdr,
                 int vector_loads, int64_t tiles, cudaStream_t st);
+// ... or, with many short segments, on the warp-per-32-segments kernel of reduce_warpseg.cu
+bool warpseg_applies(int64_t N, int64_t S);
+int warpseg_launch(int32_t dtype, int64_t H, int32_t op, const void* data, const int64_t* off, int64_t N, int64_t S,
+                   void* out, void* hdr, cudaStream_t st);
 
 // ---------------------------------------------------------------------------------------------
 // main kernel
@@ -303,6 +307,14 @@ static int run_reduce(const RedPlan& p, const void* data, const int64_t* ridx, c
   if (OpInfo<OP>::kNeedsExt) {
     segreduce_init_kernel<<<1, 1, 0, st>>>(hdr, OP == RUA_MIN);
     if ((rc = check_launch())) return rc;
+  }
+  if (p.flat && !ridx && p.vector_loads >= 1 && warpseg_applies(N, S)) {
+    // many short segments of narrow rows: every segment is finished by the lane that owns it (no pieces to merge);
+    // empty segments of sum / mean / prod are written inline, so only max / min / logsumexp need the patch pass
+    if ((rc = warpseg_launch(p.dtype, H, OP, data, off, N, S, out, hdr, st))) return rc;
+    if (!OpInfo<OP>::kNeedsExt) return RUA_OK;
+    segreduce_patch_kernel<T, V, OP><<<(unsigned)ceil_div(S * (H / V), 256), 256, 0, st>>>(off, S, H, (T*)out, hdr);
+    return check_launch();
   }
   if (N > 0) {
     if (p.col_tiles > 65535) return RUA_ERR_UNSUPPORTED;

@@ -222,10 +222,18 @@ emit_ptr_warpseg_kernel(const int64_t* __restrict__ off, int64_t S, int64_t n, i
     const int64_t w1 = w0 + kEwWin < wend ? w0 + kEwWin : wend;
     const unsigned who = __ballot_sync(kFullMask, beg <= w0 && end >= w0 + kEwWin);
     if (!who) {
-      const int lo = (int)((beg > w0 ? beg : w0) - w0), hi = (int)((end < w1 ? end : w1) - w0);
-      for (int p = lo; p < hi; ++p) own[p] = (unsigned char)lane;
+      const int64_t lo64 = beg < w0 ? w0 : (beg > w1 ? w1 : beg), hi64 = end < w0 ? w0 : (end > w1 ? w1 : end);
+      int p = (int)(lo64 - w0);
+      const int hi = (int)(hi64 - w0);
+      for (; p < hi && (p & 3); ++p) own[p] = (unsigned char)lane;          // head bytes up to a word boundary
+      const unsigned word = (unsigned)lane * 0x01010101u;
+      for (; p + 4 <= hi; p += 4) *reinterpret_cast<unsigned*>(own + p) = word;   // four positions per store
+      for (; p < hi; ++p) own[p] = (unsigned char)lane;
     }
     __syncwarp();
+    // segment starts relative to the warp's first position fit 32 bits unless the warp spans >= 2^30 positions
+    const bool small = wend - wbeg < (1ll << 30);
+    const int rel_beg = small ? (int)(beg - wbeg) : 0;
     const int groups = (int)((w1 - w0 + 3) >> 2);        // groups of 4 positions in this window (warp-uniform)
     for (int g0 = 0; g0 < groups; g0 += 32) {
       const int g = g0 + lane;
@@ -240,10 +248,13 @@ emit_ptr_warpseg_kernel(const int64_t* __restrict__ off, int64_t S, int64_t n, i
       int64_t sv[4], wv[4], fv[4];
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
-        const int64_t ob = shfl_i64(beg, o[e]);
         sv[e] = s0 + o[e];
-        wv[e] = p0 + e - ob;
-        if (flat) fv[e] = sv[e] * stride + wv[e] + shfl_i64(shift, o[e]);
+        if (small) wv[e] = (p0 + e - wbeg) - (int64_t)__shfl_sync(kFullMask, rel_beg, o[e]);   // warp-uniform branch
+        else wv[e] = p0 + e - shfl_i64(beg, o[e]);
+        if (flat) {
+          fv[e] = sv[e] * stride + wv[e];
+          if (right_align) fv[e] += shfl_i64(shift, o[e]);
+        }
       }
       if (g >= groups) continue;
       if (wide_stores && p0 >= wbeg && p0 + 4 <= w1) {

@@ -8,45 +8,49 @@
 // offset table, a block scan, three barriers: 49 M warp instructions for 32.5 M rows, 16 % of the HBM peak).  Here a
 // WARP owns 32 consecutive SEGMENTS instead:
 //   * lane i reads off[s0 + i], off[s0 + i + 1] -- two coalesced loads, no search, no decode, no block barrier;
-//   * the rows of those 32 segments are one contiguous range; the warp streams it through a private 2 KB
-//     shared-memory window with coalesced 128-bit loads (the next window is requested before the current one is reduced);
-//   * every lane then reduces ITS OWN segment out of the window: conflict-tolerant LDS + one accumulate per row,
-//     all 32 lanes busy -- about 10x fewer instructions than the tile kernel;
-//   * a window that lies entirely inside ONE long segment is reduced by the whole warp from registers (shuffle tree), so
-//     a long sequence among short ones costs bandwidth, not a serial loop;
+//   * the rows of those 32 segments are one contiguous range; the warp streams it through a private 4 KB
+//     shared-memory window, each window ONE TMA bulk copy (cp.async.bulk global -> shared, completion on a per-warp
+//     mbarrier) issued by lane 0: no per-lane load / store instructions, no registers held across the DRAM latency;
+//   * every lane then reduces ITS OWN segment out of the window, left to right, four scalars per 128-bit LDS -- all 32
+//     lanes busy, about 10x fewer instructions than the tile kernel;
+//   * a window that lies entirely inside ONE long segment is reduced by the whole warp (conflict-free reads, shuffle
+//     tree), so a long sequence among short ones costs bandwidth, not a serial loop;
 //   * every segment is finished by the lane that owns it: no cross-tile pieces, no span kernel, results stored coalesced.
 // The launcher picks this kernel when there are enough segments to fill the machine (reduce.cu: plan_reduce).
+#include <cstdlib>
+
 #include "reduce_common.cuh"
 
 namespace rua {
 
 constexpr int kWsThreads = 256;
 constexpr int kWsWarps = kWsThreads / 32;
-constexpr int kWsChunkBytes = 2048;
-constexpr int kWsVecPerLane = kWsChunkBytes / 16 / 32;   // 4
+constexpr int kWsChunkBytes = 4096;                      // 1024 fp32 scalars: the ~32 segments of a warp in ONE window
+constexpr int kWsVecPerLane = kWsChunkBytes / 16 / 32;   // 8
 
-template <typename T, int HE>
-__device__ __forceinline__ void ws_load_row(const T* p, typename Store<T>::Acc* x) {
-  constexpr int kBytes = HE * (int)sizeof(T);
-  if constexpr (kBytes == 16) {
-    const uint4 w = *reinterpret_cast<const uint4*>(p);
-    Store<T>::unpack(w, x);
-  } else if constexpr (kBytes == 8) {
-    const uint2 w = *reinterpret_cast<const uint2*>(p);
-    typename Store<T>::Acc y[16 / sizeof(T)];
-    Store<T>::unpack(make_uint4(w.x, w.y, 0u, 0u), y);
-#pragma unroll
-    for (int h = 0; h < HE; ++h) x[h] = y[h];
-  } else if constexpr (kBytes == 4) {
-    const uint32_t w = *reinterpret_cast<const uint32_t*>(p);
-    typename Store<T>::Acc y[16 / sizeof(T)];
-    Store<T>::unpack(make_uint4(w, 0u, 0u, 0u), y);
-#pragma unroll
-    for (int h = 0; h < HE; ++h) x[h] = y[h];
-  } else {
-#pragma unroll
-    for (int h = 0; h < HE; ++h) x[h] = Store<T>::to_acc(p[h]);
-  }
+// ---- TMA bulk copy (cp.async.bulk, SASS UBLKCP) global -> shared, completion on an mbarrier ---------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DONE_%=;\n"
+      "bra WAIT_%=;\n"
+      "DONE_%=:\n"
+      "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
 }
 
 template <typename A, int HE, int OP>
@@ -72,7 +76,8 @@ segreduce_warpseg_kernel(const T* __restrict__ data, const int64_t* __restrict__
   constexpr int G = E / HE;                         // rows per vector
   constexpr int CE = kWsChunkBytes / (int)sizeof(T);
   constexpr int CR = CE / HE;                       // rows per window
-  __shared__ uint4 s_buf[kWsWarps][kWsChunkBytes / 16];
+  __shared__ __align__(128) uint4 s_buf[kWsWarps][kWsChunkBytes / 16];
+  __shared__ __align__(8) uint64_t s_bar[kWsWarps];
 
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int64_t s0 = ((int64_t)blockIdx.x * kWsWarps + warp) * 32;
@@ -90,54 +95,78 @@ segreduce_warpseg_kernel(const T* __restrict__ data, const int64_t* __restrict__
     end = end < covered ? end : covered;
     const int64_t wbeg = shfl_i64(beg, 0), wend = shfl_i64(end, 31);
     const int64_t total_e = N * HE;
-    const uint4* s_mine = s_buf[warp];
-    uint4 raw[kWsVecPerLane];
+    const int64_t bulk_e = total_e & ~(int64_t)(E - 1);   // elements reachable with whole 16-byte vectors
+    uint4* s_mine = s_buf[warp];
+    const T* sb = reinterpret_cast<const T*>(s_mine);
+    uint64_t* bar = &s_bar[warp];
+    uint32_t phase = 0;
+    if (lane == 0) mbar_init(bar, 1);
+    __syncwarp();
 
-    // request the vectors of the window that starts at element e0 (a multiple of E: data is 16-byte aligned)
-    auto request = [&](int64_t e0) {
+    auto add_ext = [&](const A* x) {
+      if (OpInfo<OP>::kNeedsExt) {
 #pragma unroll
-      for (int j = 0; j < kWsVecPerLane; ++j) {
-        const int64_t e = e0 + (int64_t)(lane + 32 * j) * E;
-        raw[j] = make_uint4(0u, 0u, 0u, 0u);
-        if (e < wend * HE) {
-          if (e + E <= total_e) {
-            asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];"
-                         : "=r"(raw[j].x), "=r"(raw[j].y), "=r"(raw[j].z), "=r"(raw[j].w) : "l"(data + e));
-          } else {                                   // the last, partial vector of the array
-            T* tmp = reinterpret_cast<T*>(&raw[j]);
-#pragma unroll
-            for (int k = 0; k < E; ++k)
-              if (e + k < total_e) tmp[k] = data[e + k];
-          }
-        }
+        for (int h = 0; h < HE; ++h) ext = OP == RUA_MIN ? max_num(ext, x[h]) : min_num(ext, x[h]);
       }
     };
-
-    const int64_t e_first = (wbeg * HE) & ~(int64_t)(E - 1);
-    if (wbeg < wend) request(e_first);
-    for (int64_t e0 = e_first; e0 < wend * HE; e0 += CE) {
-      const int64_t r_lo = e0 / HE;                  // first row of the window (e0 is a multiple of E, HE divides E)
-      const int64_t r_hi = r_lo + CR < wend ? r_lo + CR : wend;
-      uint4* s_w = s_buf[warp];
+    auto add_row = [&](int r) {                      // one row out of the window (row_bytes-wide LDS)
+      A x[HE];
+      constexpr int kBytes = HE * (int)sizeof(T);
+      const T* p = sb + r * HE;
+      if constexpr (kBytes == 8) {
+        const uint2 w = *reinterpret_cast<const uint2*>(p);
+        A y[E];
+        Store<T>::unpack(make_uint4(w.x, w.y, 0u, 0u), y);
 #pragma unroll
-      for (int j = 0; j < kWsVecPerLane; ++j) s_w[lane + 32 * j] = raw[j];
+        for (int h = 0; h < HE; ++h) x[h] = y[h];
+      } else if constexpr (kBytes == 4) {
+        const uint32_t w = *reinterpret_cast<const uint32_t*>(p);
+        A y[E];
+        Store<T>::unpack(make_uint4(w, 0u, 0u, 0u), y);
+#pragma unroll
+        for (int h = 0; h < HE; ++h) x[h] = y[h];
+      } else {
+#pragma unroll
+        for (int h = 0; h < HE; ++h) x[h] = Store<T>::to_acc(p[h]);
+      }
+      acc.template add<kFast>(x);
+      add_ext(x);
+    };
+
+    for (int64_t e0 = (wbeg * HE) & ~(int64_t)(E - 1); e0 < wend * HE; e0 += CE) {   // e0: a multiple of E (data is 16-byte aligned)
+      // ---- the window [e0, e0 + CE) arrives with ONE bulk copy issued by lane 0 --------------------------------
+      const int64_t want_e = (wend * HE - e0 + (E - 1)) & ~(int64_t)(E - 1);      // up to the warp's last row, in whole vectors
+      const int64_t stop_e = e0 + (want_e < CE ? want_e : CE);
+      const int64_t bulk_stop = stop_e < bulk_e ? stop_e : bulk_e;
+      const uint32_t nbytes = bulk_stop > e0 ? (uint32_t)((bulk_stop - e0) * (int64_t)sizeof(T)) : 0u;
+      if (nbytes) {
+        if (lane == 0) {
+          mbar_expect_tx(bar, nbytes);
+          bulk_g2s(s_mine, data + e0, nbytes, bar);
+        }
+        mbar_wait(bar, phase);
+        phase ^= 1u;
+      }
+      if (stop_e > bulk_e) {                          // the last, partial vector of the whole array: element by element
+        T* st_ = reinterpret_cast<T*>(s_mine);
+        for (int64_t e = (bulk_e > e0 ? bulk_e : e0) + lane; e < total_e && e < stop_e; e += 32) st_[e - e0] = data[e];
+        __syncwarp();
+      }
+      const int64_t r_lo = e0 / HE;                  // first row of the window (HE divides E)
+      const int64_t r_hi = r_lo + CR < wend ? r_lo + CR : wend;
       // does ONE segment cover the whole window?  (at most one lane can say yes)
-      const bool covers = beg <= r_lo && end >= r_lo + CR;
-      const unsigned who = __ballot_sync(kFullMask, covers);
-      if (who) {
+      const unsigned who = __ballot_sync(kFullMask, beg <= r_lo && end >= r_lo + CR);
+      if (who) {                                     // the whole warp reduces it: 8 conflict-free 128-bit reads per lane
         St part;
         part.reset();
 #pragma unroll
         for (int j = 0; j < kWsVecPerLane; ++j) {
           A x[E];
-          Store<T>::unpack(raw[j], x);
+          Store<T>::unpack(s_mine[lane + 32 * j], x);
 #pragma unroll
           for (int g = 0; g < G; ++g) {
             part.template add<kFast>(&x[g * HE]);
-            if (OpInfo<OP>::kNeedsExt) {
-#pragma unroll
-              for (int h = 0; h < HE; ++h) ext = OP == RUA_MIN ? max_num(ext, x[g * HE + h]) : min_num(ext, x[g * HE + h]);
-            }
+            add_ext(&x[g * HE]);
           }
         }
 #pragma unroll
@@ -146,25 +175,28 @@ segreduce_warpseg_kernel(const T* __restrict__ data, const int64_t* __restrict__
           part.template merge<kFast>(other);
         }
         if (lane == __ffs(who) - 1) acc.template merge<kFast>(part);
-      }
-      if (e0 + CE < wend * HE) request(e0 + CE);     // the next window is in flight while this one is reduced
-      __syncwarp();
-      if (!who) {
-        const int64_t lo = beg > r_lo ? beg : r_lo, hi = end < r_hi ? end : r_hi;
-        const T* sb = reinterpret_cast<const T*>(s_mine) + (lo - r_lo) * HE;
-        const int n = hi > lo ? (int)(hi - lo) : 0;
-#pragma unroll 4
-        for (int r = 0; r < n; ++r) {
-          A x[HE];
-          ws_load_row<T, HE>(sb + r * HE, x);
-          acc.template add<kFast>(x);
-          if (OpInfo<OP>::kNeedsExt) {
+      } else {                                       // every lane reduces its own segment's rows, left to right
+        const int64_t lo = beg < r_lo ? r_lo : (beg > r_hi ? r_hi : beg), hi = end < r_lo ? r_lo : (end > r_hi ? r_hi : end);
+        int r = (int)(lo - r_lo);
+        const int r_end = (int)(hi - r_lo);
+        if constexpr (G > 1) {
+          for (; r < r_end && (r & (G - 1)); ++r) add_row(r);
+        }
+#pragma unroll 2
+        for (; r + G <= r_end; r += G) {             // G rows per 128-bit LDS
+          A x[E];
+          Store<T>::unpack(*reinterpret_cast<const uint4*>(sb + r * HE), x);
 #pragma unroll
-            for (int h = 0; h < HE; ++h) ext = OP == RUA_MIN ? max_num(ext, x[h]) : min_num(ext, x[h]);
+          for (int g = 0; g < G; ++g) {
+            acc.template add<kFast>(&x[g * HE]);
+            add_ext(&x[g * HE]);
           }
         }
+        if constexpr (G > 1) {
+          for (; r < r_end; ++r) add_row(r);
+        }
       }
-      __syncwarp();
+      __syncwarp();                                  // everybody is done with the window before it is overwritten
     }
 
     if (s < S) {

@@ -1000,6 +1000,111 @@ row_map_transpose_kernel(const RowMapParams p, const int TT_) {
   }
 }
 
+// The same ragged transpose for ONE-VECTOR rows (token ids, per-token scalars: BASELINE config 5), restructured around
+// what bounds it: latency.  ncu on the kernel above (8-byte rows): 94 % warps active, 36 % DRAM -- a CTA lives ~4 us for
+// 8 KB in + 8 KB out because its loads form a chain (poff[t] -> rows of P; sorted[r] -> off[i] -> rows of C) and the
+// second chain only started after the barrier.  Here (1) BOTH metadata chains are started at kernel entry, and (2) a CTA
+// owns KT time-tiles of 32 steps for its 32 ranks and issues the row loads of all of them before the first shared-
+// memory store, so the chain is paid once per KT * 8 KB and KT times as many bytes are in flight per thread.
+template <typename V, bool kFromPack, int KT>
+__global__ void __launch_bounds__(256, KT == 1 ? 8 : (KT == 2 ? 5 : 4))
+row_map_transpose1_kernel(const RowMapParams p) {
+  __shared__ V tile[KT][32][33];                     // [time tile][time step][rank] (+1: bank skew)
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int64_t r0 = (int64_t)blockIdx.x * 32, t0 = (int64_t)blockIdx.y * (32 * KT);
+  const rua_side_t& sq = kFromPack ? p.d : p.s;     // the sequence-major side
+  const int64_t B = p.rg.B, Tp = p.rg.Tp, W = sq.width;
+  const int64_t* __restrict__ poff = p.rg.poff;
+  const int64_t* __restrict__ off = p.rg.off;
+  const bool padded_dst = kFromPack && sq.layout != RUA_CAT;
+  const V* __restrict__ src = reinterpret_cast<const V*>(p.src);
+  V* __restrict__ dst = reinterpret_cast<V*>(p.dst);
+
+  // ---- both metadata chains start now ---------------------------------------------------------------------------
+  // pack side: this warp's time steps are tt = warp + 8 k of every time tile; lane (kt * 4 + k) fetches poff for it
+  int64_t my_pt = 0, my_bst = 0;
+  if (lane < 4 * KT) {
+    const int64_t t = t0 + (lane >> 2) * 32 + warp + 8 * (lane & 3);
+    if (t < Tp) { my_pt = __ldg(poff + t); my_bst = __ldg(poff + t + 1) - my_pt; }
+  }
+  // sequence side: this warp's ranks are r0 + warp + 8 k; lane k fetches sorted -> off for it
+  int64_t my_i = 0, my_o = 0, my_len = 0;
+  if (lane < 4) {
+    const int64_t r = r0 + warp + 8 * lane;
+    if (r < B) {
+      my_i = __ldg(p.rg.sorted + r);
+      my_o = __ldg(off + my_i);
+      my_len = __ldg(off + my_i + 1) - my_o;
+    }
+  }
+  // no token of this CTA exists when the batch size at its first time step does not reach its first rank
+  {
+    const int64_t bs0 = t0 < Tp ? __ldg(poff + t0 + 1) - __ldg(poff + t0) : 0;
+    if (!padded_dst && bs0 <= r0) return;           // CTA-uniform
+  }
+  auto seq_row = [&](int64_t i, int64_t o, int64_t len, int64_t t) -> int64_t {
+    return sq.layout == RUA_CAT ? o + t : (sq.layout == RUA_LEFT ? i * W + t : i * W + (W - len) + t);
+  };
+
+  V val[KT][4];
+  unsigned on = 0;                                   // bit kt * 4 + k: val[kt][k] holds a row
+  if (kFromPack) {   // ---- P -> C / L: read P along ranks ----------------------------------------------------------
+#pragma unroll
+    for (int kt = 0; kt < KT; ++kt)
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int64_t pt = shfl_i64(my_pt, kt * 4 + k), bst = shfl_i64(my_bst, kt * 4 + k);
+        if (r0 + lane < bst) {                       // bst == 0 beyond Tp
+          on |= 1u << (kt * 4 + k);
+          val[kt][k] = ld_stream(src + pt + r0 + lane);
+        }
+      }
+#pragma unroll
+    for (int kt = 0; kt < KT; ++kt)
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+        if (on >> (kt * 4 + k) & 1u) tile[kt][warp + 8 * k][lane] = val[kt][k];
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {                    // write the sequence-major side along time
+      const int64_t i = shfl_i64(my_i, k), o = shfl_i64(my_o, k), len = shfl_i64(my_len, k);
+      if (r0 + warp + 8 * k >= B) break;             // warp-uniform
+#pragma unroll
+      for (int kt = 0; kt < KT; ++kt) {
+        const int64_t t = t0 + kt * 32 + lane;
+        if (t < len) st_stream(dst + seq_row(i, o, len, t), tile[kt][lane][warp + 8 * k]);
+        else if (padded_dst && t < W) st_stream(dst + i * W + t, make_fill<V>(p.fill, 0));   // left-aligned padding
+      }
+    }
+  } else {           // ---- C / L / R -> P: read the sequence-major side along time ---------------------------------
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int64_t i = shfl_i64(my_i, k), o = shfl_i64(my_o, k), len = shfl_i64(my_len, k);
+#pragma unroll
+      for (int kt = 0; kt < KT; ++kt) {
+        const int64_t t = t0 + kt * 32 + lane;
+        if (r0 + warp + 8 * k < B && t < len) {
+          on |= 1u << (kt * 4 + k);
+          val[kt][k] = ld_stream(src + seq_row(i, o, len, t));
+        }
+      }
+    }
+#pragma unroll
+    for (int kt = 0; kt < KT; ++kt)
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+        if (on >> (kt * 4 + k) & 1u) tile[kt][lane][warp + 8 * k] = val[kt][k];
+    __syncthreads();
+#pragma unroll
+    for (int kt = 0; kt < KT; ++kt)
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int64_t pt = shfl_i64(my_pt, kt * 4 + k), bst = shfl_i64(my_bst, kt * 4 + k);
+        if (r0 + lane < bst) st_stream(dst + pt + r0 + lane, tile[kt][warp + 8 * k][lane]);
+      }
+  }
+}
+
 // can the ragged transpose serve this call?  (identity token map, untransformed lengths, narrow rows)
 static bool transpose_applies(const RowMapParams& p, int64_t* grid_y, int* tt) {
   if (p.gather_index || p.scatter_index || p.row_vecs < 1 || p.row_vecs > 7) return false;
@@ -1026,8 +1131,14 @@ static void launch_narrow(RowMapParams& p, int64_t rows, cudaStream_t st) {
     dim3 grid((unsigned)ceil_div(p.rg.B, 32), (unsigned)gy);
     const bool from_pack = p.s.layout == RUA_PACK;
     if (p.row_vecs == 1) {
-      if (from_pack) row_map_transpose_kernel<V, true, 1><<<grid, 256, 0, st>>>(p, tt);
-      else row_map_transpose_kernel<V, false, 1><<<grid, 256, 0, st>>>(p, tt);
+      // one-vector rows: KT time tiles of 32 steps per CTA, all of their row loads in flight together
+      constexpr int kMaxKT = sizeof(V) >= 16 ? 2 : 4;   // 48 KB of static shared memory
+      const int kt = gy <= 1 ? 1 : ((gy <= 2 || kMaxKT == 2) ? 2 : 4);
+      dim3 g1((unsigned)ceil_div(p.rg.B, 32), (unsigned)ceil_div(gy, kt));
+#define RUA_T1(FP_, KT_) row_map_transpose1_kernel<V, FP_, KT_><<<g1, 256, 0, st>>>(p)
+      if (from_pack) { if (kt == 1) RUA_T1(true, 1); else if (kt == 2) RUA_T1(true, 2); else RUA_T1(true, kMaxKT); }
+      else { if (kt == 1) RUA_T1(false, 1); else if (kt == 2) RUA_T1(false, 2); else RUA_T1(false, kMaxKT); }
+#undef RUA_T1
     } else {
       if (from_pack) row_map_transpose_kernel<V, true, 0><<<grid, 256, 0, st>>>(p, tt);
       else row_map_transpose_kernel<V, false, 0><<<grid, 256, 0, st>>>(p, tt);

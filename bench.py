@@ -614,6 +614,10 @@ def run_ours(args):
         }
         if gather is not None:
             line['output_gather'] = gather
+            # the curve WITH the gather SURVEY.md 8e names, beside `value` (which stays the no-gather, weak-scaling number)
+            line['value_with_output_gather'] = {'value': gather['fused_peer_store']['value'], 'unit': 'tokens/s',
+                                                'ms_per_step': gather['fused_peer_store']['ms_per_step'],
+                                                'bound': 'NVLink ingress: (N-1)/N of the global payload per rank per step'}
         emit(line)
     if world > 1:
         dist.destroy_process_group()
@@ -642,16 +646,59 @@ def time_output_gather(args, step, data, lens, lens_host, glens, parts, rank, wo
     windows = shard.PeerWindows(max_off + b_total * row)
     glens_dev = glens.to(dev)
 
+    # micro-batches of the local shard: consecutive runs of sequences with ~equal token counts.  The fused R -> C +
+    # peer-store kernel of micro-batch k runs on a side stream (NVLink-bound) while the conversions of micro-batch k+1
+    # and the reductions of micro-batch k-1 run on the main stream (HBM-bound): the wire never waits for compute.
+    kmb = max(1, min(args.gather_micro_batches, lens_host.numel()))
+    csum = torch.cumsum(lens_host, 0)
+    n_local = int(csum[-1])
+    cuts, start = [], 0
+    for k in range(kmb):
+        end = lens_host.numel() if k == kmb - 1 else int(torch.searchsorted(csum, n_local * (k + 1) // kmb, right=True))
+        end = max(end, start + 1) if start < lens_host.numel() else start
+        if end > start:
+            cuts.append((start, end, int(csum[start - 1]) if start else 0, int(csum[end - 1])))
+        start = end
+    ids_local = parts[rank].to(dev)
+    side = torch.cuda.Stream(dev)
+
     def fused_step():
         _native._CACHE.clear()
-        right = rua.C(data=data, token_sizes=lens).pack().left(0).right(0)
-        windows.fence()
-        full, back = shard.gather_catted_fused(right, parts, glens_dev, windows, local_copy=True, fence=False)
-        s = rua.segment_sum(back, lens)
-        m = rua.segment_max(back, lens)
+        cur = torch.cuda.current_stream()
+        windows.fence()                                   # peers have finished reading last step's window
+        goff, _ = _native.scan(glens_dev)                 # where every sequence of the GLOBAL batch starts
+        back = torch.empty((n_local, HIDDEN), dtype=data.dtype, device=dev)
+        s = torch.empty((lens_host.numel(), HIDDEN), dtype=data.dtype, device=dev)
+        m = torch.empty_like(s)
+        keep, landed = [], []
+
+        def reduce_part(j):
+            a, b, ta, tb = cuts[j]
+            cur.wait_event(landed[j])                     # the local copy of micro-batch j has been written
+            s[a:b] = rua.segment_sum(back[ta:tb], lens[a:b])
+            m[a:b] = rua.segment_max(back[ta:tb], lens[a:b])
+
+        for k, (a, b, ta, tb) in enumerate(cuts):
+            right = rua.C(data=data[ta:tb], token_sizes=lens[a:b]).pack().left(0).right(0)
+            ready = torch.cuda.Event()
+            ready.record(cur)
+            with torch.cuda.stream(side):
+                side.wait_event(ready)
+                shard.gather_catted_fused(right, parts, glens_dev, windows, fence=False, seq_ids=ids_local[a:b],
+                                          goff=(goff, total_tokens), local_out=back[ta:tb])
+                ev = torch.cuda.Event()
+                ev.record(side)
+            landed.append(ev)
+            keep.append(right)                            # allocated on `cur`, read on `side`: freed after the join below
+            if k > 0:
+                reduce_part(k - 1)
+        reduce_part(len(cuts) - 1)
+        cur.wait_stream(side)
+        full = windows.view((total_tokens, HIDDEN), data.dtype, 0)
         gs = shard.gather_rows_fused(s, parts, windows, offset_bytes=sum_off, fence=False)
         gm = shard.gather_rows_fused(m, parts, windows, offset_bytes=max_off, fence=False)
         windows.fence()
+        del keep
         return full, gs, gm
 
     def nccl_step():
@@ -683,7 +730,11 @@ def time_output_gather(args, step, data, lens, lens_host, glens, parts, rank, wo
     wire = (world - 1) * int(lens_host.sum()) * row
     res = {'what': 'the same step, but every rank ends with the global C data + global segment_sum / segment_max',
            'fused_peer_store': {'ms_per_step': f_ms, 'value': total_tokens / (f_ms * 1e-3), 'unit': 'tokens/s',
-                                'nvlink_out_GBs_per_rank': wire / (f_ms * 1e-3) / 1e9},
+                                'nvlink_out_GBs_per_rank': wire / (f_ms * 1e-3) / 1e9,
+                                'micro_batches': len(cuts),
+                                'ingress_floor_ms_at_900GBs': wire / 900e9 * 1e3,
+                                'how': 'per micro-batch: conversions on the main stream, fused R->C + NVLink peer stores on a '
+                                       'side stream, reductions as soon as the local copy has landed'},
            'nccl_all_gather_then_permute': {'ms_per_step': n_ms, 'value': total_tokens / (n_ms * 1e-3),
                                             'unit': 'tokens/s'},
            'results_identical': same, 'steps': steps,
@@ -730,6 +781,8 @@ def main():
     ap.add_argument('--ref-seqs', type=int, default=0, help='reference arm: sequences per step (0 = full batch if it fits the budget)')
     ap.add_argument('--ref-budget', type=float, default=200.0, help='reference arm: seconds for the whole run')
     ap.add_argument('--no-gather', action='store_true', help='skip the output-gather legs of multi-GPU runs')
+    ap.add_argument('--gather-micro-batches', type=int, default=4,
+                    help='output gather: micro-batches per step (peer stores of one overlap the conversions of the next)')
     ap.add_argument('--exchange', default='peer', choices=['peer', 'nccl', 'none'],
                     help='per-step lengths exchange of multi-GPU runs: peer-window stores (default), NCCL all-gather, or none (diagnostic)')
     args = ap.parse_args()

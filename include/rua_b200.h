@@ -115,6 +115,22 @@ size_t rua_scan_workspace_bytes(int64_t n);
 int rua_scan_lengths(const int64_t* sizes, int64_t n, int64_t clamp_max, int64_t* off, int64_t* stats,
                      void* ws, size_t ws_bytes, rua_stream_t stream);
 
+/* the same scan with two optional extras (either may be left out by passing NULL):
+ *  - sizes == NULL: the lengths are those of a PackedSequence, len[i] = #{t : bs[t] > unsorted[i]} (core/view.py:21-25
+ *    on a P source), computed on the fly and also written to len_out (n entries): P -> token_sizes + offsets in ONE launch;
+ *  - notify_host_mapped != NULL: 3 int64 of PINNED HOST memory reachable from the device (UVA).  When the scan is
+ *    complete the device writes [sum, max, ticket] there (ticket last, after a system-scope fence), so the host can
+ *    learn N = sum and T = max by polling notify[2] == ticket instead of copying stats back and synchronising the
+ *    stream.  ws: rua_scan_workspace_bytes(n). */
+int rua_scan_lengths_ex(const int64_t* sizes, int64_t n, int64_t clamp_max, int64_t* off, int64_t* stats, void* ws,
+                        size_t ws_bytes, const int64_t* bs, const int64_t* unsorted, int64_t Tp, int64_t* len_out,
+                        int64_t* notify_host_mapped, int64_t ticket, rua_stream_t stream);
+
+/* pinned host memory a kernel can write to directly (cudaHostAlloc mapped + portable): *device_ptr is what to pass as
+ * notify_host_mapped, *host_ptr is where the host polls.  Set-up calls (they synchronise like cudaMalloc / cudaFree). */
+int rua_pinned_alloc(size_t bytes, void** host_ptr, void** device_ptr);
+int rua_pinned_free(void* host_ptr);
+
 /* stable descending argsort of the lengths (ties by ascending index -- the documented deviation from
  * the reference's non-stable CPU sort, SURVEY.md 8c hazard 1) and its inverse.  T = max length. */
 size_t rua_sort_workspace_bytes(int64_t B);

@@ -38,6 +38,10 @@ SIGNATURES = {
     'rua_selftest': (c_int32, []),
     'rua_scan_workspace_bytes': (c_size_t, [c_int64]),
     'rua_scan_lengths': (c_int32, [c_void_p, c_int64, c_int64, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
+    'rua_scan_lengths_ex': (c_int32, [c_void_p, c_int64, c_int64, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p, c_void_p,
+                                      c_int64, c_void_p, c_void_p, c_int64, c_void_p]),
+    'rua_pinned_alloc': (c_int32, [c_size_t, POINTER(c_void_p), POINTER(c_void_p)]),
+    'rua_pinned_free': (c_int32, [c_void_p]),
     'rua_sort_workspace_bytes': (c_size_t, [c_int64]),
     'rua_sort_lengths': (c_int32, [c_void_p, c_int64, c_int64, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
     'rua_sort_keys': (c_int32, [c_void_p, c_int64, c_int64, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),

@@ -148,20 +148,94 @@ def scalar_bytes(value, dtype: torch.dtype) -> bytes:
 INT64_MAX = (1 << 63) - 1
 
 
-def scan(sizes: Tensor, clamp_max: int = INT64_MAX) -> Tuple[Tensor, Tensor]:
-    """(off[n+1], stats[2] = (sum, max)) of an int64 device vector; no host sync."""
+class _Notices:
+    """ring of [sum, max, ticket] slots in pinned host memory that the scan kernel writes directly (UVA mapping): the
+    host learns N and T by polling a cache line -- no device->host copy to enqueue, no stream synchronisation.  A slot is
+    reused after RING scans; a reader that finds a newer ticket falls back to copying the device-side stats."""
+    RING = 512
+    SPINS = 400000          # ~50 ms of polling before falling back to a stream synchronisation
+
+    def __init__(self):
+        lib = _lib.load()
+        host, dev = ctypes.c_void_p(), ctypes.c_void_p()
+        _lib.check(lib.rua_pinned_alloc(24 * self.RING, ctypes.byref(host), ctypes.byref(dev)), 'rua_pinned_alloc')
+        self.host, self.dev = host.value, dev.value
+        self.slots = [(ctypes.c_int64 * 3).from_address(self.host + 24 * k) for k in range(self.RING)]
+        self.count = 0
+
+    def take(self):
+        k = self.count % self.RING
+        self.count += 1
+        return self.slots[k], self.dev + 24 * k, self.count     # (host view, device address, ticket)
+
+    @classmethod
+    def read(cls, note):
+        """-> (sum, max) or None (slot reused / timed out: use the device-side stats)."""
+        slot, ticket = note
+        for _ in range(cls.SPINS):
+            seen = slot[2]
+            if seen == ticket:
+                return slot[0], slot[1]
+            if seen > ticket:
+                return None
+        return None
+
+
+_NOTICES = None
+
+
+def scan(sizes: Optional[Tensor], clamp_max: int = INT64_MAX, notify: bool = False, pack=None):
+    """(off[n+1], stats[2] = (sum, max)) of an int64 device vector; no host sync.
+
+    ``notify``: also returns a notice (third result) through which the host can read (sum, max) as soon as the kernel
+    has written them to pinned host memory.  ``pack = (bs_dev, unsorted, Tp, n)``: the vector is not given but derived
+    on the fly as the lengths of a PackedSequence (fourth result: the lengths) -- one launch instead of two."""
+    global _NOTICES
     lib = _lib.load()
-    sizes = _i64(sizes)
-    require_cuda(sizes)
-    n = sizes.numel()
-    tiles = max((n + 2047) // 2048, 1)      # == rua_scan_workspace_bytes(n) / 8
-    with _on(sizes.device):
-        # one allocation: [off (n+1) | stats (2) | tile status words (tiles)]
-        buf = torch.empty(n + 3 + tiles, dtype=torch.long, device=sizes.device)
+    if pack is None:
+        sizes = _i64(sizes)
+        require_cuda(sizes)
+        n, dev = sizes.numel(), sizes.device
+    else:
+        bs_dev, unsorted, tp, n = pack
+        dev = unsorted.device
+    tiles = (n + 4095) // 4096 + 1          # == rua_scan_workspace_bytes(n) / 8
+    note = None
+    with _on(dev):
+        # one allocation: [off (n+1) | stats (2) | tile status words + completion counter (tiles) | lengths (n, pack only)]
+        extra = n if pack is not None else 0
+        buf = torch.empty(n + 3 + tiles + extra, dtype=torch.long, device=dev)
         base = buf.data_ptr()
-        _lib.check(lib.rua_scan_lengths(sizes.data_ptr(), n, clamp_max, base, base + 8 * (n + 1),
-                                        base + 8 * (n + 3), 8 * tiles, _stream()), 'rua_scan_lengths')
-    return buf[:n + 1], buf[n + 1:n + 3]
+        note_dev, ticket = None, 0
+        if notify:
+            if _NOTICES is None:
+                _NOTICES = _Notices()
+            slot, note_dev, ticket = _NOTICES.take()
+            note = (slot, ticket)
+        if pack is None:
+            _lib.check(lib.rua_scan_lengths_ex(sizes.data_ptr(), n, clamp_max, base, base + 8 * (n + 1), base + 8 * (n + 3),
+                                               8 * tiles, None, None, 0, None, note_dev, ticket, _stream()),
+                       'rua_scan_lengths_ex')
+        else:
+            _lib.check(lib.rua_scan_lengths_ex(None, n, clamp_max, base, base + 8 * (n + 1), base + 8 * (n + 3), 8 * tiles,
+                                               bs_dev.data_ptr() if tp else None, unsorted.data_ptr(), tp,
+                                               base + 8 * (n + 3 + tiles), note_dev, ticket, _stream()),
+                       'rua_scan_lengths_ex')
+    off, stats = buf[:n + 1], buf[n + 1:n + 3]
+    if pack is not None:
+        return off, stats, note, buf[n + 3 + tiles:]
+    if notify:
+        return off, stats, note
+    return off, stats
+
+
+def scan_with_totals(sizes: Tensor) -> Tuple[Tensor, int, int]:
+    """(off[n+1], sum, max) with the two totals on the HOST (read from the scan's pinned-memory notice)."""
+    off, stats, note = scan(sizes, notify=True)
+    got = _Notices.read(note)
+    if got is None:
+        got = fetch(stats).tolist()
+    return off, int(got[0]), int(got[1])
 
 
 @dataclass
@@ -184,15 +258,19 @@ class Ragged:
     _keep: list = field(default_factory=list)
     _spec_ok: bool = False            # the speculative early launch of _ensure_pack_fused held
     _stream: Optional[int] = None     # the stream the producer kernels were enqueued on (see _cache_get)
+    _note: Optional[tuple] = None     # (pinned host slot, ticket) of the scan's completion notice
 
     def mark_ready(self):
         with _on(self.device):
             self._stream = _stream()
 
     def _sync_stats(self):
-        # the one inherent D2H: output shapes depend on device data (16 bytes, pinned, stream-ordered)
-        n, t = fetch(self.stats).tolist()
-        self._N, self._T = int(n), int(t)
+        # the one inherent device -> host dependency: output shapes depend on device data.  The scan kernel has written
+        # (N, T) into pinned host memory on its own; poll that, and only copy the stats back if the notice is gone.
+        got = _Notices.read(self._note) if self._note is not None else None
+        if got is None:
+            got = fetch(self.stats).tolist()
+        self._N, self._T = int(got[0]), int(got[1])
 
     @property
     def N(self) -> int:
@@ -337,8 +415,8 @@ def ragged_from_lengths(token_sizes: Tensor, want_pack: bool = False, early=None
         rg = Ragged(device=dev, B=b, len=lens, off=torch.empty(b + 1, dtype=torch.long, device=dev))
         rg._ensure_pack_fused(early)
     else:
-        off, stats = scan(lens)
-        rg = Ragged(device=dev, B=b, len=lens, off=off, stats=stats)
+        off, stats, note = scan(lens, notify=True)
+        rg = Ragged(device=dev, B=b, len=lens, off=off, stats=stats, _note=note)
         if want_pack:
             rg.ensure_pack()
     _cache_put(token_sizes, 'len', rg)
@@ -381,10 +459,8 @@ def ragged_from_pack(batch_sizes: Tensor, sorted_indices: Optional[Tensor], unso
             unsorted = _i64(unsorted_indices)
             srt = _i64(sorted_indices)
         require_cuda(unsorted, srt)
-        lens = torch.empty(B, dtype=torch.long, device=device)
-        _lib.check(lib.rua_lengths_from_pack(bs_dev.data_ptr() if Tp else None, unsorted.data_ptr(), B, Tp,
-                                             lens.data_ptr(), _stream()), 'rua_lengths_from_pack')
-    off, stats = scan(lens)
+    # lengths of the P (one binary search per sequence) and their prefix sum in ONE launch
+    off, stats, _, lens = scan(None, pack=(bs_dev, unsorted, Tp, B))
     rg = Ragged(device=device, B=B, len=lens, off=off, stats=stats, _N=int(host[-1]) if Tp else 0, _T=Tp,
                 sorted=srt, unsorted=unsorted, bs_dev=bs_dev, poff=poff, bs_cpu=batch_sizes, Tp=Tp)
     rg._keep.append(devbuf)

@@ -11,6 +11,8 @@
 // rows for C / P), and every row bounds-checked.  rua_gather_rows / rua_scatter_rows then move the payload.
 //
 // Also here: the per-device counter of out-of-range explicit indices (shared by rowmap.cu).
+#include <cstring>
+
 #include "common.cuh"
 
 namespace rua {
@@ -96,6 +98,26 @@ int rua_token_rows(const rua_ragged_t* ragged, const rua_side_t* side, int64_t T
   token_rows_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(rg, *side, T, batch_ptr, token_ptr, n, rows_out,
                                                                        index_error_counter());
   return check_launch();
+}
+
+/* pinned host memory that kernels can write directly (UVA mapping): the completion notices of rua_scan_lengths_ex */
+int rua_pinned_alloc(size_t bytes, void** host_ptr, void** device_ptr) {
+  if (!host_ptr || !device_ptr || bytes == 0) return RUA_ERR_INVALID;
+  void* h = nullptr;
+  int rc = check_cuda(cudaHostAlloc(&h, bytes, cudaHostAllocMapped | cudaHostAllocPortable));
+  if (rc) return rc;
+  void* d = nullptr;
+  rc = check_cuda(cudaHostGetDevicePointer(&d, h, 0));
+  if (rc) { cudaFreeHost(h); return rc; }
+  memset(h, 0, bytes);
+  *host_ptr = h;
+  *device_ptr = d;
+  return RUA_OK;
+}
+
+int rua_pinned_free(void* host_ptr) {
+  if (!host_ptr) return RUA_OK;
+  return check_cuda(cudaFreeHost(host_ptr));
 }
 
 int rua_index_error_count(int64_t* count_host, int32_t reset) {

@@ -55,9 +55,25 @@ __device__ __forceinline__ int64_t warp_max(int64_t v) {
 }
 
 // status word: (value << 2) | flag; flag 0 = not ready, 1 = tile aggregate, 2 = inclusive prefix
+// optional extras of the scan (rua_scan_lengths_ex):
+//   * lengths derived on the fly from a PackedSequence's (batch_sizes, unsorted_indices): len[i] = first t with
+//     bs[t] <= unsorted[i] (bs is non-increasing) -- P -> token_sizes and its prefix sum in ONE launch;
+//   * completion notice straight into pinned host memory: the last CTA to finish writes [sum, max, ticket] through
+//     the UVA mapping, so the host learns N and T by polling one cache line instead of enqueueing a device->host copy
+//     and synchronising the stream (the output shapes of most conversions depend on them).
+struct ScanExtras {
+  const int64_t* bs;
+  const int64_t* unsorted;
+  int64_t Tp;
+  int64_t* len_out;
+  volatile int64_t* notify;   // device-accessible pinned host memory, 3 x int64, or NULL
+  int64_t ticket;
+  int64_t tiles;
+};
+
 __global__ void __launch_bounds__(kScanThreads)
 scan_kernel(const int64_t* __restrict__ in, int64_t n, int64_t clamp_max, int64_t* __restrict__ out,
-            int64_t* __restrict__ stats, unsigned long long* status, int multi_tile) {
+            int64_t* __restrict__ stats, unsigned long long* status, int multi_tile, const ScanExtras ex) {
   __shared__ int64_t s_warp[kScanThreads / 32];
   __shared__ int64_t s_wmax[kScanThreads / 32];
   __shared__ int64_t s_prefix;
@@ -71,7 +87,21 @@ scan_kernel(const int64_t* __restrict__ in, int64_t n, int64_t clamp_max, int64_
 #pragma unroll
   for (int k = 0; k < kScanItems; ++k) {
     int64_t idx = base + k;
-    v[k] = idx < n ? in[idx] : 0;
+    if (in) {
+      v[k] = idx < n ? in[idx] : 0;
+    } else {
+      v[k] = 0;
+      if (idx < n) {
+        const int64_t r = __ldg(ex.unsorted + idx);
+        int64_t lo = 0, hi = ex.Tp;
+        while (lo < hi) {
+          const int64_t mid = (lo + hi) >> 1;
+          if (__ldg(ex.bs + mid) > r) lo = mid + 1; else hi = mid;
+        }
+        v[k] = lo;
+        ex.len_out[idx] = lo;
+      }
+    }
     tsum += v[k];
     tmax = v[k] > tmax ? v[k] : tmax;
   }
@@ -131,12 +161,35 @@ scan_kernel(const int64_t* __restrict__ in, int64_t n, int64_t clamp_max, int64_
     if (multi_tile) atomicMax((long long*)(stats + 1), (long long)bmax);
     else stats[1] = bmax;
   }
+  if (ex.notify) {                                   // kernel-uniform
+    __syncthreads();                                 // this CTA's stats contributions are issued
+    if (tid == 0) {
+      bool last = true;
+      if (multi_tile) {
+        __threadfence();
+        last = atomicAdd(status + ex.tiles, 1ull) == (unsigned long long)(ex.tiles - 1);
+        __threadfence();
+      }
+      if (last) {
+        ex.notify[0] = *(volatile int64_t*)(stats);
+        ex.notify[1] = *(volatile int64_t*)(stats + 1);
+        __threadfence_system();
+        ex.notify[2] = ex.ticket;
+      }
+    }
+  }
 }
 
-__global__ void scan_empty_kernel(int64_t* out, int64_t* stats) {
+__global__ void scan_empty_kernel(int64_t* out, int64_t* stats, volatile int64_t* notify, int64_t ticket) {
   out[0] = 0;
   stats[0] = 0;
   stats[1] = 0;
+  if (notify) {
+    notify[0] = 0;
+    notify[1] = 0;
+    __threadfence_system();
+    notify[2] = ticket;
+  }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -368,34 +421,44 @@ int64_t rua_launch_count(void) { return (int64_t)g_launch_count; }
 
 size_t rua_scan_workspace_bytes(int64_t n) {
   int64_t tiles = n > 0 ? ceil_div(n, kScanTile) : 1;
-  return (size_t)tiles * sizeof(unsigned long long);
+  return (size_t)(tiles + 1) * sizeof(unsigned long long);   // tile status words + the completion counter
 }
 
 int rua_scan_lengths(const int64_t* sizes, int64_t n, int64_t clamp_max, int64_t* off, int64_t* stats, void* ws,
                      size_t ws_bytes, rua_stream_t stream) {
-  if (n < 0 || !off || !stats || (n > 0 && !sizes)) return RUA_ERR_INVALID;
+  return rua_scan_lengths_ex(sizes, n, clamp_max, off, stats, ws, ws_bytes, nullptr, nullptr, 0, nullptr, nullptr, 0,
+                             stream);
+}
+
+int rua_scan_lengths_ex(const int64_t* sizes, int64_t n, int64_t clamp_max, int64_t* off, int64_t* stats, void* ws,
+                        size_t ws_bytes, const int64_t* bs, const int64_t* unsorted, int64_t Tp, int64_t* len_out,
+                        int64_t* notify_host_mapped, int64_t ticket, rua_stream_t stream) {
+  if (n < 0 || !off || !stats) return RUA_ERR_INVALID;
+  if (n > 0 && !sizes && (!unsorted || !len_out || Tp < 0 || (Tp > 0 && !bs))) return RUA_ERR_INVALID;
   cudaStream_t st = (cudaStream_t)stream;
+  ScanExtras ex{bs, unsorted, Tp, len_out, notify_host_mapped, ticket, 0};
   if (n == 0) {
-    scan_empty_kernel<<<1, 1, 0, st>>>(off, stats);
+    scan_empty_kernel<<<1, 1, 0, st>>>(off, stats, ex.notify, ticket);
     return check_launch();
   }
   int64_t tiles = ceil_div(n, kScanTile);
+  ex.tiles = tiles;
   int multi = tiles > 1;
   if (multi) {
     if (!ws || ws_bytes < rua_scan_workspace_bytes(n)) return RUA_ERR_WORKSPACE;
     int rc;
     if ((char*)stats + 2 * sizeof(int64_t) == (char*)ws) {
       // stats sits right in front of the status words (the layout torchrua_b200 uses): one memset
-      rc = check_cuda(cudaMemsetAsync(stats, 0, 2 * sizeof(int64_t) + (size_t)tiles * sizeof(unsigned long long), st));
+      rc = check_cuda(cudaMemsetAsync(stats, 0, 2 * sizeof(int64_t) + (size_t)(tiles + 1) * sizeof(unsigned long long), st));
       if (rc) return rc;
     } else {
-      rc = check_cuda(cudaMemsetAsync(ws, 0, (size_t)tiles * sizeof(unsigned long long), st));
+      rc = check_cuda(cudaMemsetAsync(ws, 0, (size_t)(tiles + 1) * sizeof(unsigned long long), st));
       if (rc) return rc;
       rc = check_cuda(cudaMemsetAsync(stats, 0, 2 * sizeof(int64_t), st));
       if (rc) return rc;
     }
   }
-  scan_kernel<<<(unsigned)tiles, kScanThreads, 0, st>>>(sizes, n, clamp_max, off, stats, (unsigned long long*)ws, multi);
+  scan_kernel<<<(unsigned)tiles, kScanThreads, 0, st>>>(sizes, n, clamp_max, off, stats, (unsigned long long*)ws, multi, ex);
   return check_launch();
 }
 

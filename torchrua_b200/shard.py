@@ -239,8 +239,20 @@ def _pointer_array(values):
     return (ctypes.c_void_p * len(values))(*[v if v else None for v in values])
 
 
+def global_offsets(global_lengths: Tensor, device: torch.device) -> Tuple[Tensor, int]:
+    """(exclusive prefix sum of the GLOBAL lengths on `device`, total token count): where every sequence of the batch
+    starts in the global C data.  Compute once per batch and hand it to the gathers of its micro-batches."""
+    from torchrua_b200 import _native
+    gl = global_lengths.to(device, non_blocking=True)
+    goff, gstats = _native.scan(gl)
+    n_total = int(global_lengths.sum()) if not global_lengths.is_cuda else int(_native.fetch(gstats)[0])
+    return goff, n_total
+
+
 def gather_catted_fused(z, parts: List[Tensor], global_lengths: Tensor, windows: PeerWindows,
-                        offset_bytes: int = 0, local_copy: bool = False, fence: bool = True):
+                        offset_bytes: int = 0, local_copy: bool = False, fence: bool = True,
+                        seq_ids: Optional[Tensor] = None, goff: Optional[Tuple[Tensor, int]] = None,
+                        local_out: Optional[Tensor] = None):
     """fused conversion + exchange (2): ``z`` is this rank's shard in ANY layout (C, L, P or R; sequences in
     the order of ``parts[rank]``).  ONE kernel reads every local token once and stores it at its place in
     the global C data (original sequence order) inside the window of every rank -- and, with
@@ -248,7 +260,12 @@ def gather_catted_fused(z, parts: List[Tensor], global_lengths: Tensor, windows:
     Returns the global (N, *) tensor (a view of this rank's window; valid after the trailing fence),
     or (global, local) with ``local_copy``.  ``fence=False`` leaves both fences to the caller (several
     gathers into disjoint parts of the window can share one pair: ``windows.fence()`` before the first store
-    and after the last)."""
+    and after the last).
+
+    Micro-batches: ``z`` may hold only SOME of this rank's sequences -- ``seq_ids`` (device int64) are their GLOBAL
+    sequence ids, ``goff`` = ``global_offsets(...)`` of the whole batch (computed once), ``local_out`` the slice of the
+    local C buffer that receives the contiguous copy.  Launched on a side stream, the peer stores of micro-batch k
+    then overlap the conversions of micro-batch k+1 (NVLink-bound and HBM-bound work share the GPU)."""
     import ctypes
 
     from torchrua_b200 import _lib, _native
@@ -263,15 +280,22 @@ def gather_catted_fused(z, parts: List[Tensor], global_lengths: Tensor, windows:
     row_bytes = src.element_size()
     for f in feat:
         row_bytes *= f
-    gl = global_lengths.to(dev, non_blocking=True)
-    goff, gstats = _native.scan(gl)                               # exclusive prefix sum of the GLOBAL lengths
-    base = goff[parts[windows.rank].to(dev, non_blocking=True)]   # first global row of each local sequence
-    n_total = int(global_lengths.sum()) if not global_lengths.is_cuda else int(_native.fetch(gstats)[0])
+    if goff is None:
+        goff = global_offsets(global_lengths, dev)
+    goff, n_total = goff
+    ids = seq_ids if seq_ids is not None else parts[windows.rank].to(dev, non_blocking=True)
+    base = goff[ids]                                              # first global row of each local sequence
     out = windows.view((n_total,) + feat, src.dtype, offset_bytes)
     dsts = [p + offset_bytes for p in windows.ptrs]
     bases = [base.data_ptr()] * windows.world
     local = None
-    if local_copy:
+    if local_out is not None:
+        if not local_out.is_contiguous() or local_out.shape[0] != rg.N:
+            raise RuntimeError('torchrua_b200: local_out must be a contiguous (tokens of z, *) buffer')
+        local = local_out
+        dsts.append(local.data_ptr())
+        bases.append(None)
+    elif local_copy:
         local = torch.empty((rg.N,) + feat, dtype=src.dtype, device=dev)
         dsts.append(local.data_ptr())
         bases.append(None)
@@ -285,7 +309,8 @@ def gather_catted_fused(z, parts: List[Tensor], global_lengths: Tensor, windows:
                    'rua_row_map_multi')
     if fence:
         windows.fence()      # every rank's rows have landed everywhere
-    return (out, local) if local_copy else out
+    base.record_stream(torch.cuda.current_stream(dev))
+    return (out, local) if (local_copy or local_out is not None) else out
 
 
 def gather_rows_fused(local_rows: Tensor, parts: List[Tensor], windows: PeerWindows, offset_bytes: int = 0,

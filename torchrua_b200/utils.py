@@ -22,10 +22,9 @@ def get_offsets(sizes: Tensor) -> Tensor:
 
 def major_sizes_to_ptr(sizes: Tensor) -> Tuple[Tensor, Tensor]:
     """(position within segment, segment id) for every element of the segmented range, in that order
-    (utils.py:7-13).  One emit kernel; the total comes from the scan's stats (one 16-byte D2H)."""
+    (utils.py:7-13).  One emit kernel; the total is read from the scan kernel's pinned-memory notice."""
     _native.require_cuda(sizes)
-    off, stats = _native.scan(sizes)
-    n = int(stats[0])
+    off, n, _ = _native.scan_with_totals(sizes)
     which, within, _ = _native.emit_ptr(off, n)
     return within, which
 

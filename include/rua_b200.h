@@ -183,6 +183,16 @@ int rua_row_map(const void* src, void* dst, int64_t row_bytes, const rua_ragged_
                 int64_t tmap_arg, int32_t pad_mode, const void* fill_host, int32_t fill_bytes,
                 rua_stream_t stream);
 
+/* fused consumer pattern: `X.left(fill)` AND `X.mask(zero, one, dtype)` (torchrua/core/cast.py:19-32 +
+ * torchrua/mask.py:6-32, e.g. padded activations + the additive attention bias of fmask) from ONE decode of the
+ * destination rows: rua_row_map towards a LEFT destination that also writes mask_out[i, t] (dst_side->rows elements of
+ * mask_elem_bytes) = one where the row holds a token, zero where it is padding.  Rows of >= 128 bytes only (narrow
+ * rows: RUA_ERR_UNSUPPORTED -- launch rua_row_map and rua_mask). */
+int rua_row_map_mask(const void* src, void* dst, int64_t row_bytes, const rua_ragged_t* ragged,
+                     const rua_side_t* src_side, const rua_side_t* dst_side, const void* fill_host, int32_t fill_bytes,
+                     const void* zero_host, const void* one_host, int32_t mask_elem_bytes, void* mask_out,
+                     rua_stream_t stream);
+
 /* constructors C/L/P/R.new(list) (torchrua/core/__init__.py:9-36): rua_row_map with an identity token map whose
  * SOURCE is a list -- sequence i is its own contiguous (len[i], row_bytes) allocation src_list[i].  src_list is a
  * DEVICE array of B device pointers; src_align = a power of two that divides every non-null pointer in it (the
@@ -190,6 +200,13 @@ int rua_row_map(const void* src, void* dst, int64_t row_bytes, const rua_ragged_
 int rua_row_map_list(const void* const* src_list, int32_t src_align, void* dst, int64_t row_bytes,
                      const rua_ragged_t* ragged, const rua_side_t* dst_side, const void* fill_host,
                      int32_t fill_bytes, rua_stream_t stream);
+
+/* compose (torchrua/compose.py:9-33: torch.cat(data)[indices]) without materialising the concatenation: dst[j] = row
+ * index[j] of the VIRTUAL concatenation of n_src tensors.  src_list: DEVICE array of n_src device pointers (whole
+ * contiguous (rows_k, row_bytes) tensors); bases: DEVICE array of n_src + 1 int64, bases[k] = first row of tensor k in the
+ * concatenation, bases[n_src] = total rows; src_align as in rua_row_map_list.  Every payload byte moves once. */
+int rua_gather_rows_multi(const void* const* src_list, const int64_t* bases, int32_t n_src, int32_t src_align,
+                          const int64_t* index, int64_t n, int64_t row_bytes, void* dst, rua_stream_t stream);
 
 /* dst[j] = src[index[j]] for j < n   (tensor_getitem / Z-keyed getitem, core/get.py:11-31).
  * Negative indices wrap (index + src_rows) like torch advanced indexing; an index that is still out of range is

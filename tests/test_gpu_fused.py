@@ -1,0 +1,105 @@
+"""SURVEY.md 8(f)-4 fused consumer patterns and 8(f)-2 compose in one launch.
+
+left_mask / left_bmask / left_fmask: padded data + mask from ONE decode (rua_row_map_mask) must be bit-identical to the
+separate `X.left(fill)` and `X.mask(...)` calls (which the golden / live-reference tests pin to the reference).
+compose: the multi-source gather (rua_gather_rows_multi) must give what `torch.cat(data)[indices]` gives
+(torchrua/compose.py:33), forward and backward."""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope='module')
+def rua():
+    import torchrua_b200
+    return torchrua_b200
+
+
+def build(rua, kind, c):
+    return {'C': lambda: c, 'L': lambda: c.left(0), 'R': lambda: c.right(0), 'P': lambda: c.pack()}[kind]()
+
+
+@pytest.mark.parametrize('kind', 'CLPR')
+@pytest.mark.parametrize('feat,dtype', [((64,), torch.float32), ((1024,), torch.bfloat16), ((3, 24), torch.float16),
+                                        ((8,), torch.float32), ((), torch.float32), ((33,), torch.float64)])
+def test_left_mask_equals_left_plus_mask(rua, kind, feat, dtype):
+    g = torch.Generator().manual_seed(3)
+    lens = torch.randint(1, 40, (57,), generator=g)
+    data = torch.randn((int(lens.sum()),) + feat, generator=g).to(dtype).cuda()
+    z = build(rua, kind, rua.C(data=data, token_sizes=lens.cuda()))
+    for fill, zero, one, mdt in ((0, False, True, torch.bool), (-2.5, -1, 3, torch.long), (1, 0.5, -0.25, torch.float16)):
+        left, m = z.left_mask(fill, zero=zero, one=one, dtype=mdt)
+        ref_left, ref_m = z.left(fill), z.mask(zero=zero, one=one, dtype=mdt)
+        assert type(left) is type(ref_left) and torch.equal(left.token_sizes, ref_left.token_sizes)
+        assert left.data.shape == ref_left.data.shape and torch.equal(left.data, ref_left.data)
+        assert m.dtype == ref_m.dtype and m.shape == ref_m.shape and torch.equal(m, ref_m)
+    left, m = z.left_bmask(7)
+    assert torch.equal(left.data, z.left(7).data) and torch.equal(m, z.bmask())
+    left, m = z.left_fmask()
+    assert torch.equal(left.data, z.left(0).data) and torch.equal(m, z.fmask())
+    cu = z.cu_seqlens()
+    assert cu.dtype == torch.int32 and torch.equal(cu.cpu().long(), torch.cat([torch.zeros(1, dtype=torch.long), lens.cumsum(0)]))
+
+
+def test_left_mask_keeps_gradients(rua):
+    lens = torch.tensor([3, 1, 4]).cuda()
+    x = torch.randn(8, 64, device='cuda', requires_grad=True)
+    left, m = rua.C(data=x, token_sizes=lens).left_fmask()
+    w = torch.randn_like(left.data)
+    (left.data * w).sum().backward()
+    bp, tp = rua.C(data=x.detach(), token_sizes=lens).ptr()
+    assert torch.equal(x.grad, w[bp, tp])
+
+
+def test_left_mask_cfg2_shape(rua):
+    """BASELINE configs[1] shape: the fused launch writes B*T mask bytes on top of the conversion's traffic."""
+    g = torch.Generator().manual_seed(0)
+    lens = torch.randint(1, 513, (4096,), generator=g)
+    data = torch.randn((int(lens.sum()), 1024), device='cuda').to(torch.bfloat16)
+    c = rua.C(data=data, token_sizes=lens.cuda())
+    for z in (c, c.pack()):
+        left, m = z.left_fmask()
+        assert torch.equal(left.data, z.left(0).data) and torch.equal(m, z.fmask())
+
+
+@pytest.mark.parametrize('feat,dtype', [((16,), torch.float32), ((256,), torch.bfloat16), ((), torch.long)])
+def test_compose_is_cat_then_index(rua, feat, dtype):
+    """compose(batches) == pack of all sequences of all batches; the payload rows come straight from every source
+    (C, L, P, R storage) in one launch."""
+    from torch.nn.utils.rnn import pack_sequence
+    g = torch.Generator().manual_seed(5)
+    batches, seqs = [], []
+    for k, kind in enumerate('CLPRC'):
+        lens = torch.randint(1, 9, (4 + k,), generator=g)
+        n = int(lens.sum())
+        data = (torch.randn((n,) + feat, generator=g) * 10).to(dtype).cuda()
+        seqs += list(data.split(lens.tolist()))
+        batches.append(build(rua, kind, rua.C(data=data, token_sizes=lens.cuda())))
+    p = rua.compose(batches)
+    # canonical form: the sequences in their original order
+    c = p.cat()
+    assert torch.equal(c.data, torch.cat(seqs, dim=0))
+    assert torch.equal(c.token_sizes.cpu(), torch.tensor([s.shape[0] for s in seqs]))
+    ref = pack_sequence(seqs, enforce_sorted=False)
+    assert torch.equal(p.batch_sizes, ref.batch_sizes)
+
+
+def test_compose_backward_reaches_every_source(rua):
+    g = torch.Generator().manual_seed(6)
+    leaves, batches = [], []
+    for k, kind in enumerate('CLPR'):
+        lens = torch.randint(1, 6, (3 + k,), generator=g)
+        x = torch.randn((int(lens.sum()), 32), generator=g).cuda().requires_grad_(True)
+        leaves.append(x)
+        batches.append(build(rua, kind, rua.C(data=x, token_sizes=lens.cuda())))
+    p = rua.compose(batches)
+    w = torch.randn_like(p.data)
+    (p.data * w).sum().backward()
+    # every token appears exactly once in the result: its gradient is the weight at its packed position
+    cat_w = rua.P(data=w, batch_sizes=p.batch_sizes, sorted_indices=p.sorted_indices,
+                  unsorted_indices=p.unsorted_indices).cat().data
+    at = 0
+    for x in leaves:
+        assert torch.equal(x.grad, cat_w[at:at + x.shape[0]])
+        at += x.shape[0]

@@ -56,8 +56,11 @@ SIGNATURES = {
                                  c_void_p]),
     'rua_row_map': (c_int32, [c_void_p, c_void_p, c_int64, POINTER(Ragged), POINTER(Side), POINTER(Side),
                               c_int32, c_int64, c_int32, c_char_p, c_int32, c_void_p]),
+    'rua_row_map_mask': (c_int32, [c_void_p, c_void_p, c_int64, POINTER(Ragged), POINTER(Side), POINTER(Side), c_char_p, c_int32,
+                                   c_char_p, c_char_p, c_int32, c_void_p, c_void_p]),
     'rua_row_map_list': (c_int32, [c_void_p, c_int32, c_void_p, c_int64, POINTER(Ragged), POINTER(Side), c_char_p,
                                    c_int32, c_void_p]),
+    'rua_gather_rows_multi': (c_int32, [c_void_p, c_void_p, c_int32, c_int32, c_void_p, c_int64, c_int64, c_void_p, c_void_p]),
     'rua_gather_rows': (c_int32, [c_void_p, c_int64, c_void_p, c_int64, c_int64, c_void_p, c_void_p]),
     'rua_scatter_rows': (c_int32, [c_void_p, c_void_p, c_int64, c_int64, c_void_p, c_int64, c_void_p]),
     'rua_token_rows': (c_int32, [POINTER(Ragged), POINTER(Side), c_int64, c_void_p, c_void_p, c_int64, c_void_p, c_void_p]),

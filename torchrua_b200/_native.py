@@ -588,6 +588,37 @@ class _RowMap(torch.autograd.Function):
         return grad_src, None, None
 
 
+def row_map_mask(src_flat: Tensor, spec: MapSpec, fill_value, zero, one, mask_dtype: torch.dtype):
+    """padded (LEFT) destination AND its (B, W) mask from one decode (rua_row_map_mask); None when the fused kernel does
+    not apply (narrow rows, gradients wanted) -- the caller then issues the two launches."""
+    lib = _lib.load()
+    require_cuda(src_flat)
+    if src_flat.requires_grad and torch.is_grad_enabled():
+        return None
+    feat = tuple(src_flat.shape[1:])
+    row_bytes = src_flat.element_size()
+    for f in feat:
+        row_bytes *= f
+    rows = spec.dst.rows
+    if row_bytes < 128 or rows == 0 or spec.dst.layout != LEFT:
+        return None
+    flat = src_flat if src_flat.is_contiguous() else src_flat.contiguous()
+    out = torch.empty((rows,) + feat, dtype=flat.dtype, device=flat.device)
+    mask_out = torch.empty((rows,), dtype=mask_dtype, device=flat.device)
+    fill = scalar_bytes(fill_value, flat.dtype)
+    z, o = scalar_bytes(zero, mask_dtype), scalar_bytes(one, mask_dtype)
+    rg, sd, dd = spec.rg.c_struct(), spec.src.c_struct(), spec.dst.c_struct()
+    with _on(flat.device):
+        prof = _profile_begin()
+        _lib.check(lib.rua_row_map_mask(_ptr(flat), out.data_ptr(), row_bytes, ctypes.byref(rg), ctypes.byref(sd),
+                                        ctypes.byref(dd), fill, len(fill), z, o, mask_out.element_size(),
+                                        mask_out.data_ptr(), _stream()), 'rua_row_map_mask')
+        if prof is not None:
+            tokens = min(spec.src.rows, rows) if spec.rg._N is None else min(spec.rg._N, spec.src.rows, rows)
+            _profile_end(prof, 'row_map_mask', (tokens + rows) * row_bytes + rows * mask_out.element_size() + 8 * spec.rg.B)
+    return out, mask_out
+
+
 def row_map(src_flat: Tensor, spec: MapSpec, fill_value=0) -> Tensor:
     """src_flat: (rows_src, *feat) contiguous flattened storage of the source layout."""
     require_cuda(src_flat)
@@ -849,6 +880,74 @@ def gather_rows(src: Tensor, index: Tensor) -> Tensor:
             flat = flat.contiguous()
         return _gather_rows_raw(flat, _i64(index)).view(tuple(index.shape) + tuple(flat.shape[1:]))
     return _GatherRows.apply(src, index)
+
+
+class _GatherRowsMulti(torch.autograd.Function):
+    """rows ``index`` of the VIRTUAL concatenation of several (rows_k, *feat) tensors -- compose (torchrua/compose.py:33:
+    ``torch.cat(data, dim=0)[indices]``) without the concatenation pass: every payload byte moves once."""
+
+    @staticmethod
+    def forward(ctx, index: Tensor, *payloads: Tensor):
+        out, bases = _gather_rows_multi_raw(index, [p.detach() for p in payloads])
+        ctx.save_for_backward(index)
+        ctx.bases = bases
+        ctx.shapes = [tuple(p.shape) for p in payloads]
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_out: Tensor):
+        (index,) = ctx.saved_tensors
+        total = ctx.bases[-1]
+        g = grad_out.contiguous()
+        feat = tuple(g.shape[1:])
+        # compose's index visits every live row exactly once (padding rows of L / R sources: never): one scatter into
+        # the concatenated gradient, whose slices are the gradients of the sources (views, no copies)
+        cat = torch.zeros((total,) + feat, dtype=g.dtype, device=g.device)
+        if index.numel() > 0:
+            _scatter_rows_raw(cat, _i64(index).view(-1), g)
+        grads = tuple(cat[ctx.bases[k]:ctx.bases[k + 1]].view(shape) for k, shape in enumerate(ctx.shapes))
+        return (None,) + grads
+
+
+def _gather_rows_multi_raw(index: Tensor, payloads):
+    lib = _lib.load()
+    flats = [p if p.is_contiguous() else p.contiguous() for p in payloads]
+    dev = flats[0].device
+    feat = tuple(flats[0].shape[1:])
+    dtype = flats[0].dtype
+    for f in flats:
+        if tuple(f.shape[1:]) != feat or f.dtype != dtype or f.device != dev:
+            raise RuntimeError('torchrua_b200: compose needs sequences of one dtype, device and feature shape')
+    bases = [0]
+    for f in flats:
+        bases.append(bases[-1] + f.shape[0])
+    ptrs = [f.data_ptr() for f in flats]
+    bits = 0
+    for q in ptrs:
+        bits |= q
+    align = 32
+    while bits % align:
+        align >>= 1
+    idx = _i64(index).view(-1)
+    out = torch.empty((idx.numel(),) + feat, dtype=dtype, device=dev)
+    if out.numel() > 0:
+        row_bytes = out.element_size()
+        for f in feat:
+            row_bytes *= f
+        k = len(flats)
+        table = upload(torch.tensor(ptrs + bases, dtype=torch.long), dev)      # [pointers (k) | bases (k + 1)], one H2D
+        with _on(dev):
+            _lib.check(lib.rua_gather_rows_multi(table.data_ptr(), table.data_ptr() + 8 * k, k, align, idx.data_ptr(),
+                                                 idx.numel(), row_bytes, out.data_ptr(), _stream()),
+                       'rua_gather_rows_multi')
+    return out, bases
+
+
+def gather_rows_multi(index: Tensor, payloads) -> Tensor:
+    require_cuda(index, *payloads)
+    if torch.is_grad_enabled() and any(p.requires_grad for p in payloads):
+        return _GatherRowsMulti.apply(index, *payloads)
+    return _gather_rows_multi_raw(index, payloads)[0]
 
 
 def _bump_version(t: Tensor) -> None:

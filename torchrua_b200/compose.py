@@ -6,7 +6,10 @@ Two nested packings, both done by the native kernels:
     (stable descending device sort, one row-map launch over the int64 row indices);
   * OUTER: the per-batch sequence counts are packed too, which yields the order in which a consumer
     (e.g. an RNN over "sequences of sequences") wants the sequences back.
-The result's unsorted_indices is the composition of the two permutations; the payload is gathered once.
+The result's unsorted_indices is the composition of the two permutations.  The payload moves ONCE: the reference
+concatenates every source (one read + one write of all payload bytes) and then gathers (another read + write); here
+one multi-source launch (rua_gather_rows_multi) reads each row from the tensor it lives in and writes it to its place
+in the packed result.
 """
 from typing import List
 
@@ -35,7 +38,7 @@ def compose(sequences: List[Z]) -> P:
 
     unsorted_indices = inner.unsorted_indices[outer.data]
     return P(
-        data=_native.gather_rows(torch.cat(payloads, dim=0), inner.data),
+        data=_native.gather_rows_multi(inner.data, payloads),      # no torch.cat pass: rows come straight from each source
         batch_sizes=inner.batch_sizes,
         sorted_indices=_native.invert_permutation(unsorted_indices),
         unsorted_indices=unsorted_indices,

@@ -15,6 +15,7 @@
 // payload byte is read twice: traffic = N*D read + rows_dst*D written (+ metadata).
 // HBM-bound; no shared memory (no reuse) and no tensor cores (nothing to contract).
 #include <cstdlib>
+#include <cstring>
 
 #include "common.cuh"
 #include "tile_decode.cuh"
@@ -38,6 +39,10 @@ struct RowMapParams {
   const int64_t* gather_index;   // explicit source rows (rua_gather_rows) or NULL
   const int64_t* scatter_index;  // explicit destination rows (rua_scatter_rows) or NULL
   unsigned long long* index_errors;   // device counter of out-of-range explicit indices (rows skipped / zero-filled)
+  // fused mask (rua_row_map_mask): one element per DESTINATION ROW, `one` where the row holds a token, else `zero`
+  void* mask_out;
+  int32_t mask_elem;                  // 1, 2, 4 or 8 bytes
+  unsigned long long mask_zero, mask_one;
   uint32_t div_wrv_m, div_wrv_s;  // narrow padded destinations: x / (width * row_vecs) for x < 2^31 (FastDiv)
   uint32_t div_rv_m, div_rv_s;    //                             x / row_vecs
 };
@@ -270,6 +275,13 @@ row_map_kernel(const RowMapParams p) {
         srow = drow == kNoRow ? kNoRow : j;
       }
       else { srow = map_row(p, j); drow = j; }
+      if (p.mask_out && blockIdx.y == 0) {           // the same decode feeds the mask: coalesced, one element per lane
+        const unsigned long long m = srow >= 0 ? p.mask_one : p.mask_zero;
+        if (p.mask_elem == 1) reinterpret_cast<uint8_t*>(p.mask_out)[j] = (uint8_t)m;
+        else if (p.mask_elem == 2) reinterpret_cast<uint16_t*>(p.mask_out)[j] = (uint16_t)m;
+        else if (p.mask_elem == 4) reinterpret_cast<uint32_t*>(p.mask_out)[j] = (uint32_t)m;
+        else reinterpret_cast<unsigned long long*>(p.mask_out)[j] = m;
+      }
       if (srow == kPadRow && p.pad_mode == RUA_PAD_ROW0) srow = 0;
     }
   }
@@ -340,9 +352,12 @@ __device__ __forceinline__ bool decode_dst(const RowMapParams& p, int64_t j, int
   return td >= 0 && td < base_len;
 }
 
+// With p.gather_index the list holds n_src whole TENSORS instead (compose, torchrua/compose.py:9-33): destination row j
+// copies row index[j] of their virtual concatenation, bases[k] = first row of tensor k in it (bases[n_src] = total).
 template <typename V>
 __global__ void __launch_bounds__(kRowMapThreads)
-row_map_list_kernel(const RowMapParams p, const uint8_t* const* __restrict__ src_list, int64_t row_bytes) {
+row_map_list_kernel(const RowMapParams p, const uint8_t* const* __restrict__ src_list, int64_t row_bytes,
+                    const int64_t* __restrict__ bases = nullptr, int n_src = 0) {
   const int lane = threadIdx.x & 31;
   const int64_t warp = (int64_t)blockIdx.x * (kRowMapThreads / 32) + (threadIdx.x >> 5);
   const int rpw = p.rows_per_warp;
@@ -354,8 +369,25 @@ row_map_list_kernel(const RowMapParams p, const uint8_t* const* __restrict__ src
   {
     const int64_t j = j0 + lane;
     if (lane < rpw && j < rows) {
-      int64_t i, td, len;
-      saddr = decode_dst(p, j, i, td, len) ? (long long)__ldg(reinterpret_cast<const unsigned long long*>(src_list) + i) + td * row_bytes : 0;
+      if (p.gather_index) {
+        const int64_t total = __ldg(bases + n_src);
+        int64_t r = __ldg(p.gather_index + j);
+        if (r < 0) r += total;
+        if (r < 0 || r >= total) {                     // out of range: zero row, counted (see checked_index)
+          if (p.index_errors) atomicAdd(p.index_errors, 1ull);
+          saddr = 0;
+        } else {
+          int lo = 0, hi = n_src;
+          while (hi - lo > 1) {
+            const int mid = (lo + hi) >> 1;
+            if (__ldg(bases + mid) <= r) lo = mid; else hi = mid;
+          }
+          saddr = (long long)__ldg(reinterpret_cast<const unsigned long long*>(src_list) + lo) + (r - __ldg(bases + lo)) * row_bytes;
+        }
+      } else {
+        int64_t i, td, len;
+        saddr = decode_dst(p, j, i, td, len) ? (long long)__ldg(reinterpret_cast<const unsigned long long*>(src_list) + i) + td * row_bytes : 0;
+      }
     }
   }
   const int lpr = p.lanes_per_row;
@@ -1221,12 +1253,14 @@ static int launch_row_map(RowMapParams& p, int64_t row_bytes, int64_t rows, cuda
                           p.pad_mode == RUA_PAD_FILL && p.s.len_xform == RUA_LEN_SAME && p.d.len_xform == RUA_LEN_SAME;
   const bool padded_side = (p.s.layout == RUA_CAT && (p.d.layout == RUA_LEFT || p.d.layout == RUA_RIGHT)) ||
                            (p.d.layout == RUA_CAT && (p.s.layout == RUA_LEFT || p.s.layout == RUA_RIGHT));
-  const bool run_copy = simple_map && padded_side && row_bytes < 512 && (a & 15u) == 0 && ((uintptr_t)p.dst & 63u) == 0;
+  const bool run_copy = simple_map && padded_side && row_bytes < 512 && (a & 15u) == 0 && ((uintptr_t)p.dst & 63u) == 0 &&
+                        !p.mask_out;   // the fused mask lives in the wide-row kernel
   if (run_copy && row_bytes >= 128) {
     vec = 16;
     p.row_vecs = row_bytes / vec;
   }
   if (row_bytes < 128 || run_copy) {  // narrow rows: tile kernels (segment offsets staged in shared memory)
+    if (p.mask_out) return RUA_ERR_UNSUPPORTED;   // callers launch rua_mask separately for narrow rows
     if (ceil_div(rows * p.row_vecs, kTileVecs) >= (1ll << 31)) return RUA_ERR_UNSUPPORTED;
     switch (vec) {
       case 16: launch_narrow<uint4>(p, rows, st); break;
@@ -1268,7 +1302,7 @@ static int launch_row_map(RowMapParams& p, int64_t row_bytes, int64_t rows, cuda
 }
 
 static int launch_row_map_list(RowMapParams& p, const uint8_t* const* src_list, int src_align, int64_t row_bytes,
-                               int64_t rows, cudaStream_t st) {
+                               int64_t rows, cudaStream_t st, const int64_t* bases = nullptr, int n_src = 0) {
   if (rows <= 0 || row_bytes <= 0) return RUA_OK;
   uintptr_t a = (uintptr_t)p.dst | (uintptr_t)row_bytes | (uintptr_t)src_align;
   int vec = row_bytes >= 128 ? 32 : 16;
@@ -1289,12 +1323,12 @@ static int launch_row_map_list(RowMapParams& p, const uint8_t* const* src_list, 
   if (blocks >= (1ll << 31)) return RUA_ERR_UNSUPPORTED;
   dim3 grid((unsigned)blocks, (unsigned)splits);
   switch (vec) {
-    case 32: row_map_list_kernel<V256><<<grid, kRowMapThreads, 0, st>>>(p, src_list, row_bytes); break;
-    case 16: row_map_list_kernel<uint4><<<grid, kRowMapThreads, 0, st>>>(p, src_list, row_bytes); break;
-    case 8: row_map_list_kernel<uint2><<<grid, kRowMapThreads, 0, st>>>(p, src_list, row_bytes); break;
-    case 4: row_map_list_kernel<unsigned int><<<grid, kRowMapThreads, 0, st>>>(p, src_list, row_bytes); break;
-    case 2: row_map_list_kernel<unsigned short><<<grid, kRowMapThreads, 0, st>>>(p, src_list, row_bytes); break;
-    default: row_map_list_kernel<unsigned char><<<grid, kRowMapThreads, 0, st>>>(p, src_list, row_bytes); break;
+    case 32: row_map_list_kernel<V256><<<grid, kRowMapThreads, 0, st>>>(p, src_list, row_bytes, bases, n_src); break;
+    case 16: row_map_list_kernel<uint4><<<grid, kRowMapThreads, 0, st>>>(p, src_list, row_bytes, bases, n_src); break;
+    case 8: row_map_list_kernel<uint2><<<grid, kRowMapThreads, 0, st>>>(p, src_list, row_bytes, bases, n_src); break;
+    case 4: row_map_list_kernel<unsigned int><<<grid, kRowMapThreads, 0, st>>>(p, src_list, row_bytes, bases, n_src); break;
+    case 2: row_map_list_kernel<unsigned short><<<grid, kRowMapThreads, 0, st>>>(p, src_list, row_bytes, bases, n_src); break;
+    default: row_map_list_kernel<unsigned char><<<grid, kRowMapThreads, 0, st>>>(p, src_list, row_bytes, bases, n_src); break;
   }
   return check_launch();
 }
@@ -1376,6 +1410,41 @@ int rua_row_map(const void* src, void* dst, int64_t row_bytes, const rua_ragged_
   p.fill = make_uint4(((uint32_t*)pat)[0], ((uint32_t*)pat)[1], ((uint32_t*)pat)[2], ((uint32_t*)pat)[3]);
   p.gather_index = nullptr;
   p.scatter_index = nullptr;
+  return launch_row_map(p, row_bytes, dst_side->rows, (cudaStream_t)stream);
+}
+
+int rua_row_map_mask(const void* src, void* dst, int64_t row_bytes, const rua_ragged_t* ragged,
+                     const rua_side_t* src_side, const rua_side_t* dst_side, const void* fill_host, int32_t fill_bytes,
+                     const void* zero_host, const void* one_host, int32_t mask_elem_bytes, void* mask_out,
+                     rua_stream_t stream) {
+  if (!ragged || !valid_side(src_side) || !valid_side(dst_side) || row_bytes < 0) return RUA_ERR_INVALID;
+  if (dst_side->layout != RUA_LEFT || dst_side->len_xform != RUA_LEN_SAME || src_side->len_xform != RUA_LEN_SAME) return RUA_ERR_INVALID;
+  if (mask_elem_bytes != 1 && mask_elem_bytes != 2 && mask_elem_bytes != 4 && mask_elem_bytes != 8) return RUA_ERR_INVALID;
+  if (dst_side->rows == 0) return RUA_OK;
+  if (!dst || !mask_out || !zero_host || !one_host || !ragged->off || ragged->B <= 0) return RUA_ERR_INVALID;
+  if (row_bytes < 128) return RUA_ERR_UNSUPPORTED;
+  bool uses_pack = src_side->layout == RUA_PACK;
+  if (uses_pack && (!ragged->poff || !ragged->sorted || !ragged->unsorted)) return RUA_ERR_INVALID;
+  if (!src && src_side->rows > 0) return RUA_ERR_INVALID;
+  if (fill_bytes != 0 && fill_bytes != 1 && fill_bytes != 2 && fill_bytes != 4 && fill_bytes != 8 && fill_bytes != 16)
+    return RUA_ERR_INVALID;
+  if (fill_bytes > 0 && (!fill_host || row_bytes % fill_bytes != 0)) return RUA_ERR_INVALID;
+  RowMapParams p{};
+  p.src = (const uint8_t*)src;
+  p.dst = (uint8_t*)dst;
+  p.rg = *ragged;
+  p.s = *src_side;
+  p.d = *dst_side;
+  p.tmap = RUA_MAP_SHIFT;
+  p.pad_mode = RUA_PAD_FILL;
+  uint8_t pat[16] = {0};
+  if (fill_bytes > 0)
+    for (int k = 0; k < 16; ++k) pat[k] = ((const uint8_t*)fill_host)[k % fill_bytes];
+  p.fill = make_uint4(((uint32_t*)pat)[0], ((uint32_t*)pat)[1], ((uint32_t*)pat)[2], ((uint32_t*)pat)[3]);
+  p.mask_out = mask_out;
+  p.mask_elem = mask_elem_bytes;
+  memcpy(&p.mask_zero, zero_host, mask_elem_bytes);
+  memcpy(&p.mask_one, one_host, mask_elem_bytes);
   return launch_row_map(p, row_bytes, dst_side->rows, (cudaStream_t)stream);
 }
 
@@ -1475,6 +1544,20 @@ int rua_row_map_list(const void* const* src_list, int32_t src_align, void* dst, 
     for (int k = 0; k < 16; ++k) pat[k] = ((const uint8_t*)fill_host)[k % fill_bytes];
   p.fill = make_uint4(((uint32_t*)pat)[0], ((uint32_t*)pat)[1], ((uint32_t*)pat)[2], ((uint32_t*)pat)[3]);
   return launch_row_map_list(p, (const uint8_t* const*)src_list, src_align, row_bytes, dst_side->rows, (cudaStream_t)stream);
+}
+
+int rua_gather_rows_multi(const void* const* src_list, const int64_t* bases, int32_t n_src, int32_t src_align,
+                          const int64_t* index, int64_t n, int64_t row_bytes, void* dst, rua_stream_t stream) {
+  if (n < 0 || row_bytes < 0 || n_src < 0) return RUA_ERR_INVALID;
+  if (n == 0 || row_bytes == 0) return RUA_OK;
+  if (!src_list || !bases || !index || !dst || n_src == 0) return RUA_ERR_INVALID;
+  if (src_align < 1 || (src_align & (src_align - 1))) return RUA_ERR_INVALID;
+  RowMapParams p{};
+  p.dst = (uint8_t*)dst;
+  p.d.rows = n;
+  p.gather_index = index;
+  p.index_errors = index_error_counter();
+  return launch_row_map_list(p, (const uint8_t* const*)src_list, src_align, row_bytes, n, (cudaStream_t)stream, bases, n_src);
 }
 
 /* host-only self test of the launch-time arithmetic (no GPU needed; run by the CPU test-suite): the magic-number

@@ -77,10 +77,14 @@ def test_compose_is_cat_then_index(rua, feat, dtype):
         seqs += list(data.split(lens.tolist()))
         batches.append(build(rua, kind, rua.C(data=data, token_sizes=lens.cuda())))
     p = rua.compose(batches)
-    # canonical form: the sequences in their original order
+    # canonical form: p.cat() lists the sequences in the order of the OUTER packing (compose.py:22-26: first sequence of
+    # every batch, batches by descending size, then the second ones, ...)
+    counts = [len(z.cat().token_sizes) for z in batches]
+    starts = [sum(counts[:k]) for k in range(len(counts))]
+    outer = pack_sequence([torch.arange(a, a + n) for a, n in zip(starts, counts)], enforce_sorted=False).data.tolist()
     c = p.cat()
-    assert torch.equal(c.data, torch.cat(seqs, dim=0))
-    assert torch.equal(c.token_sizes.cpu(), torch.tensor([s.shape[0] for s in seqs]))
+    assert torch.equal(c.data, torch.cat([seqs[j] for j in outer], dim=0))
+    assert torch.equal(c.token_sizes.cpu(), torch.tensor([seqs[j].shape[0] for j in outer]))
     ref = pack_sequence(seqs, enforce_sorted=False)
     assert torch.equal(p.batch_sizes, ref.batch_sizes)
 
@@ -97,9 +101,14 @@ def test_compose_backward_reaches_every_source(rua):
     w = torch.randn_like(p.data)
     (p.data * w).sum().backward()
     # every token appears exactly once in the result: its gradient is the weight at its packed position
-    cat_w = rua.P(data=w, batch_sizes=p.batch_sizes, sorted_indices=p.sorted_indices,
-                  unsorted_indices=p.unsorted_indices).cat().data
-    at = 0
-    for x in leaves:
-        assert torch.equal(x.grad, cat_w[at:at + x.shape[0]])
-        at += x.shape[0]
+    # the same weights pushed through the INVERSE route: w as a P -> cat (outer order) -> per-sequence pieces
+    from torch.nn.utils.rnn import pack_sequence
+    wp = rua.P(data=w, batch_sizes=p.batch_sizes, sorted_indices=p.sorted_indices, unsorted_indices=p.unsorted_indices)
+    pieces = wp.split()
+    counts = [len(z.cat().token_sizes) for z in batches]
+    starts = [sum(counts[:k]) for k in range(len(counts))]
+    outer = pack_sequence([torch.arange(a, a + n) for a, n in zip(starts, counts)], enforce_sorted=False).data.tolist()
+    by_seq = {j: piece for j, piece in zip(outer, pieces)}
+    for k, x in enumerate(leaves):
+        exp = torch.cat([by_seq[j] for j in range(starts[k], starts[k] + counts[k])], dim=0)
+        assert torch.equal(x.grad, exp)

@@ -13,6 +13,12 @@
 
 namespace rua {
 
+// narrow rows + many short segments: the warp-per-32-segments twin in reduce_warpseg.cu
+bool flat_supported(int32_t dtype, int64_t H);
+bool warpseg_applies(int64_t N, int64_t S);
+int warpseg_bwd_launch(int32_t dtype, int64_t H, int32_t op, const void* gout, const void* out, const void* data,
+                       const int64_t* off, int64_t N, int64_t S, void* grad, cudaStream_t st);
+
 constexpr int kBwdUnroll = 4;
 
 template <typename T, int V>
@@ -246,6 +252,12 @@ int rua_segment_reduce_backward(const void* grad_out, const void* out, const voi
   uintptr_t a = (uintptr_t)grad_out | (uintptr_t)out | (uintptr_t)data | (uintptr_t)grad_data;
   bool vec = (H % full == 0) && (a & 15u) == 0;
   cudaStream_t st = (cudaStream_t)stream;
+  if (flat_supported(dtype, H) && warpseg_applies(N, S) && (((uintptr_t)data | (uintptr_t)grad_data) & 15u) == 0) {
+    // rows no segment owns (sum of sizes < N) get no gradient; the kernel only writes rows it owns
+    int rc = check_cuda(cudaMemsetAsync(grad_data, 0, 0, st));
+    if (rc) return rc;
+    return warpseg_bwd_launch(dtype, H, op, grad_out, out, data, off, N, S, grad_data, st);
+  }
   switch (dtype) {
     case RUA_F32: return bwd_vec<float>(vec, op, grad_out, out, data, off, N, S, H, grad_data, ws, st);
     case RUA_F64: return bwd_vec<double>(vec, op, grad_out, out, data, off, N, S, H, grad_data, ws, st);

@@ -1065,8 +1065,14 @@ row_map_transpose1_kernel(const RowMapParams p) {
     const int64_t r = r0 + warp + 8 * lane;
     if (r < B) {
       my_i = __ldg(p.rg.sorted + r);
-      my_o = __ldg(off + my_i);
-      my_len = __ldg(off + my_i + 1) - my_o;
+      if (p.rg.rank_meta) {                            // one coalesced 16-byte load instead of the chain sorted -> off
+        const longlong2 m = __ldg(reinterpret_cast<const longlong2*>(p.rg.rank_meta) + r);
+        my_o = m.x;
+        my_len = m.y;
+      } else {
+        my_o = __ldg(off + my_i);
+        my_len = __ldg(off + my_i + 1) - my_o;
+      }
     }
   }
   // no token of this CTA exists when the batch size at its first time step does not reach its first rank

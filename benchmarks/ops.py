@@ -244,6 +244,16 @@ def cfg5(results, reps, quiet=False):
     row(results, 5, 'segment_sum (H=1 fp32)', 4 * n + 4 * b + 8 * b, n, lambda: rua.segment_sum(fdata, lc), reps,
         aten=lambda: torch.segment_reduce(fdata, 'sum', lengths=lc, unsafe=True))
     row(results, 5, 'segment_max (H=1 fp32)', 4 * n + 4 * b + 8 * b, n, lambda: rua.segment_max(fdata, lc), reps)
+    # backward of the per-token-scalar reductions (api time of the backward alone; graph built outside the timed region)
+    leaf = fdata.clone().requires_grad_(True)
+
+    def bwd(fn, nbytes, name):
+        out = fn(leaf, lc)
+        gout = torch.ones_like(out)
+        row(results, 5, name, nbytes, n, lambda: torch.autograd.grad(out, leaf, gout, retain_graph=True), reps)
+    bwd(rua.segment_sum, 4 * n + 4 * b + 8 * b, 'bwd segment_sum (H=1 fp32)')
+    bwd(rua.segment_max, 2 * (2 * 4 * n) + 2 * 4 * b + 8 * b, 'bwd segment_max (H=1 fp32)')
+    bwd(rua.segment_logsumexp, 2 * 4 * n + 2 * 4 * b + 8 * b, 'bwd segment_logsumexp (H=1 fp32)')
 
 
 def main():

@@ -218,6 +218,11 @@ emit_ptr_warpseg_kernel(const int64_t* __restrict__ off, int64_t S, int64_t n, i
   end = end < n ? end : n;
   const int64_t wbeg = shfl_i64(beg, 0), wend = shfl_i64(end, 31);
   unsigned char* own = s_own[warp];
+  // segment starts relative to the warp's first position fit 32 bits unless the warp spans >= 2^30 positions
+  const bool small = wend - wbeg < (1ll << 30);
+  const int rel_beg = small ? (int)(beg - wbeg) : 0;
+  // flat[p] = which * stride + within + shift = (p - wbeg) + flat_c[owner]: one 64-bit shuffle + one add per position
+  const int64_t flat_c = flat ? s * stride + shift - (beg - wbeg) : 0;
   for (int64_t w0 = wbeg & ~(int64_t)3; w0 < wend; w0 += kEwWin) {
     const int64_t w1 = w0 + kEwWin < wend ? w0 + kEwWin : wend;
     const unsigned who = __ballot_sync(kFullMask, beg <= w0 && end >= w0 + kEwWin);
@@ -231,9 +236,6 @@ emit_ptr_warpseg_kernel(const int64_t* __restrict__ off, int64_t S, int64_t n, i
       for (; p < hi; ++p) own[p] = (unsigned char)lane;
     }
     __syncwarp();
-    // segment starts relative to the warp's first position fit 32 bits unless the warp spans >= 2^30 positions
-    const bool small = wend - wbeg < (1ll << 30);
-    const int rel_beg = small ? (int)(beg - wbeg) : 0;
     const int groups = (int)((w1 - w0 + 3) >> 2);        // groups of 4 positions in this window (warp-uniform)
     for (int g0 = 0; g0 < groups; g0 += 32) {
       const int g = g0 + lane;
@@ -245,16 +247,16 @@ emit_ptr_warpseg_kernel(const int64_t* __restrict__ off, int64_t S, int64_t n, i
         o[0] = b.x & 31; o[1] = b.y & 31; o[2] = b.z & 31; o[3] = b.w & 31;   // unpainted bytes: any lane, never stored
       }
       const int64_t p0 = w0 + 4 * (int64_t)g;
+      const int64_t q0 = p0 - wbeg;                       // position relative to the warp's first one
       int64_t sv[4], wv[4], fv[4];
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
-        sv[e] = s0 + o[e];
-        if (small) wv[e] = (p0 + e - wbeg) - (int64_t)__shfl_sync(kFullMask, rel_beg, o[e]);   // warp-uniform branch
-        else wv[e] = p0 + e - shfl_i64(beg, o[e]);
-        if (flat) {
-          fv[e] = sv[e] * stride + wv[e];
-          if (right_align) fv[e] += shfl_i64(shift, o[e]);
+        if (which) sv[e] = s0 + o[e];
+        if (within) {
+          if (small) wv[e] = (q0 + e) - (int64_t)__shfl_sync(kFullMask, rel_beg, o[e]);   // warp-uniform branches
+          else wv[e] = p0 + e - shfl_i64(beg, o[e]);
         }
+        if (flat) fv[e] = (q0 + e) + shfl_i64(flat_c, o[e]);
       }
       if (g >= groups) continue;
       if (wide_stores && p0 >= wbeg && p0 + 4 <= w1) {

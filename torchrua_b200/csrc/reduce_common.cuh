@@ -5,8 +5,6 @@
 #include <cuda_fp16.h>
 #include <math_constants.h>
 
-#include <type_traits>
-
 #include "common.cuh"
 
 namespace rua {
@@ -231,23 +229,6 @@ __device__ __forceinline__ float ex2_approx(float x) {
   return r;
 }
 
-// packed bf16 pairs: one HFMA2.BF16 and ONE MUFU.EX2 for two elements (sm_90+)
-__device__ __forceinline__ uint32_t bf16x2_fma(uint32_t a, uint32_t b, uint32_t c) {
-  uint32_t d;
-  asm("fma.rn.bf16x2 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
-  return d;
-}
-__device__ __forceinline__ uint32_t bf16x2_ex2(uint32_t a) {
-  uint32_t d;
-  asm("ex2.approx.ftz.bf16x2 %0, %1;" : "=r"(d) : "r"(a));
-  return d;
-}
-__device__ __forceinline__ uint32_t bf16x2_pack(float lo, float hi) {   // round to nearest even
-  uint32_t d;
-  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
-  return d;
-}
-
 // logsumexp over kRows rows that all belong to the current segment: a[] = running max, s[] = running
 // sum of exp(x - a).  One EX2 per element (plus one per column for the rescale).
 template <typename T, int V, int kRows>
@@ -284,47 +265,11 @@ __device__ __forceinline__ void lse_batch(const Raw<T, V>* raw, typename Store<T
       }
     }
   }
-  if constexpr (std::is_same<T, __nv_bfloat16>::value && V == 8) {
-    // bf16 storage (tolerance 1e-2, output quantum 2^-9): the exponent arguments are formed and exponentiated as
-    // PACKED bf16 pairs -- per pair one HFMA2.BF16 (x * log2e - o) and one MUFU.EX2 instead of two FFMA + two MUFU; the
-    // sum stays fp32.  The reference point o of a column is bf16(max * log2e), and the running "max" kept in the state
-    // is o / log2e, so the state is self-consistent (merge / finalize only need SOME reference point near the maximum):
-    // lse = a + ln(s) exactly for the s that was accumulated.  Term errors: 2^-9 relative on the argument and on the
-    // result, plus 0.18 % on (x - max) from log2e rounded to bf16 -- all below the bf16 quantum of the output.
-    constexpr float kLog2e = 1.4426950408889634f, kLn2 = 0.6931471805599453f;
-    constexpr uint32_t kLog2e2 = 0x3FB93FB9u;         // bf16(log2 e) = 1.4453125, twice
-    uint32_t o2[4];
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      float ob[2];
-#pragma unroll
-      for (int h = 0; h < 2; ++h) {
-        const int v = 2 * j + h;
-        const float m_new = max_nan(a[v], bm[v]);
-        ob[h] = m_new * kLog2e;
-      }
-      o2[j] = bf16x2_pack(ob[0], ob[1]);
-      Pk<T>::unpack(o2[j], ob[0], ob[1]);             // the rounded reference points, as fp32
-#pragma unroll
-      for (int h = 0; h < 2; ++h) {
-        const int v = 2 * j + h;
-        s[v] = s[v] == 0.f ? 0.f : s[v] * ex2_approx(fmaf(a[v], kLog2e, -ob[h]));
-        a[v] = ob[h] * kLn2;
-      }
-      o2[j] ^= 0x80008000u;                           // -o, packed
-    }
-#pragma unroll
-    for (int k = 0; k < kRows; ++k) {
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const uint32_t e2 = bf16x2_ex2(bf16x2_fma(word_of(raw[k].r, j), kLog2e2, o2[j]));
-        float lo, hi;
-        Pk<T>::unpack(e2, lo, hi);
-        s[2 * j] += lo;
-        s[2 * j + 1] += hi;
-      }
-    }
-  } else if constexpr (sizeof(A) == 4) {
+  // (tried in round 2: exponent arguments formed and exponentiated as PACKED bf16 pairs -- fma.rn.bf16x2 +
+  // ex2.approx.ftz.bf16x2.  On sm_100a the packed ex2 is NOT one MUFU: SASS shows two MUFU.EX2.BF16 + PRMT + FMUL per
+  // pair, 9 instructions per pair against 8 for the fp32 form below, and cfg3 logsumexp went 84.6 % -> 82.8 % of peak
+  // while losing accuracy.  Dropped; profiles/r2_ncu_lse.md has the instruction mix.)
+  if constexpr (sizeof(A) == 4) {
     constexpr float kLog2e = 1.4426950408889634f;
     float mb[V];
 #pragma unroll
@@ -354,6 +299,85 @@ __device__ __forceinline__ void lse_batch(const Raw<T, V>* raw, typename Store<T
       unpack_raw<T, V>(raw[k], x);
 #pragma unroll
       for (int v = 0; v < V; ++v) s[v] += exp(x[v] - a[v]);
+    }
+  }
+}
+
+
+// the same for the rows [lo, hi) of a batch only (a segment boundary falls inside the batch): every row keeps its static
+// register index, rows outside the range are predicated off.  Replaces the per-element online update (one exp, two
+// selects and a rescale per element) that boundary batches used to fall back to.
+template <typename T, int V, int kRows>
+__device__ __forceinline__ void lse_batch_range(const Raw<T, V>* raw, int lo, int hi, typename Store<T>::Acc* a,
+                                                typename Store<T>::Acc* s, typename Store<T>::Acc& ext, uint32_t* ext2) {
+  using A = typename Store<T>::Acc;
+  A bm[V];
+  if constexpr (Pk<T>::kHas && V == 8) {
+    constexpr uint32_t kNegInf = Pk<T>::kPosInf | 0x80008000u;
+    uint32_t m2[4] = {kNegInf, kNegInf, kNegInf, kNegInf};
+#pragma unroll
+    for (int k = 0; k < kRows; ++k) {
+      if (k >= lo && k < hi) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const uint32_t w = word_of(raw[k].r, j);
+          m2[j] = Pk<T>::max_nan(m2[j], w);
+          ext2[j] = Pk<T>::min_num(ext2[j], w);
+        }
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) Pk<T>::unpack(m2[j], bm[2 * j], bm[2 * j + 1]);
+  } else {
+#pragma unroll
+    for (int v = 0; v < V; ++v) bm[v] = -inf_of<A>();
+#pragma unroll
+    for (int k = 0; k < kRows; ++k) {
+      if (k >= lo && k < hi) {
+        A x[V];
+        unpack_raw<T, V>(raw[k], x);
+#pragma unroll
+        for (int v = 0; v < V; ++v) {
+          bm[v] = max_nan(bm[v], x[v]);
+          ext = min_num(ext, x[v]);
+        }
+      }
+    }
+  }
+  if constexpr (sizeof(A) == 4) {
+    constexpr float kLog2e = 1.4426950408889634f;
+    float mb[V];
+#pragma unroll
+    for (int v = 0; v < V; ++v) {
+      float m_new = max_nan(a[v], bm[v]);
+      s[v] = s[v] == 0.f ? 0.f : s[v] * ex2_approx((a[v] - m_new) * kLog2e);
+      a[v] = m_new;
+      mb[v] = m_new * kLog2e;
+    }
+#pragma unroll
+    for (int k = 0; k < kRows; ++k) {
+      if (k >= lo && k < hi) {
+        A x[V];
+        unpack_raw<T, V>(raw[k], x);
+#pragma unroll
+        for (int v = 0; v < V; ++v) s[v] += ex2_approx(fmaf(x[v], kLog2e, -mb[v]));
+      }
+    }
+  } else {
+#pragma unroll
+    for (int v = 0; v < V; ++v) {
+      A m_new = max_nan(a[v], bm[v]);
+      s[v] = s[v] == A(0) ? A(0) : s[v] * exp(a[v] - m_new);
+      a[v] = m_new;
+    }
+#pragma unroll
+    for (int k = 0; k < kRows; ++k) {
+      if (k >= lo && k < hi) {
+        A x[V];
+        unpack_raw<T, V>(raw[k], x);
+#pragma unroll
+        for (int v = 0; v < V; ++v) s[v] += exp(x[v] - a[v]);
+      }
     }
   }
 }

@@ -79,8 +79,6 @@ typedef struct {
   const int64_t* sorted;   /* B: sorted_indices; NULL if no P side                            */
   const int64_t* unsorted; /* B: unsorted_indices; NULL if no P side                          */
   int64_t Tp;              /* number of time steps in poff (len(batch_sizes)); 0 if no P side */
-  const int64_t* rank_meta; /* optional, 2*B: (off[sorted[r]], len[sorted[r]]) per rank r (rua_rank_meta); NULL = the
-                               kernels chase sorted -> off themselves.  Only the narrow-row P conversions read it. */
 } rua_ragged_t;
 
 /* one side (source or destination) of a row map */
@@ -149,12 +147,6 @@ int rua_bucket_offsets(const int64_t* keys, const int64_t* sorted, int64_t n, in
 
 /* out[perm[j]] = j */
 int rua_invert_permutation(const int64_t* perm, int64_t B, int64_t* out, rua_stream_t stream);
-
-/* rank_meta[2r] = off[sorted[r]], rank_meta[2r+1] = off[sorted[r]+1] - off[sorted[r]]: where the r-th longest sequence
- * starts and how long it is.  The ragged transposes (P <-> C/L/R with rows of <= 16 bytes) are latency chains
- * sorted[r] -> off[i] -> rows; with this table (built once per batch, cached with the metadata) the chain is one
- * coalesced 16-byte load. */
-int rua_rank_meta(const int64_t* off, const int64_t* sorted, int64_t B, int64_t* rank_meta, rua_stream_t stream);
 
 /* bs[t] = #{i : len[i] > t}, t in [0,T), given ANY permutation `sorted` that orders len
  * non-increasingly (ours or an injected one). */

@@ -17,7 +17,7 @@ LIB = os.path.join(ROOT, 'torchrua_b200', 'lib', 'librua_b200.so')
 
 class Ragged(Structure):            # rua_ragged_t
     _fields_ = [('B', c_int64), ('off', c_void_p), ('poff', c_void_p),
-                ('sorted', c_void_p), ('unsorted', c_void_p), ('Tp', c_int64), ('rank_meta', c_void_p)]
+                ('sorted', c_void_p), ('unsorted', c_void_p), ('Tp', c_int64)]
 
 
 class Side(Structure):              # rua_side_t
@@ -52,7 +52,7 @@ def cat_pack_to_left(lib, data, token_sizes, fill_value=0):    # torchrua/core/c
     n, t = stats.tolist()
     b = token_sizes.numel()
     out = data.new_empty((b, t, *data.shape[1:]))
-    rg = Ragged(b, off.data_ptr(), None, None, None, 0, None)
+    rg = Ragged(b, off.data_ptr(), None, None, None, 0)
     src, dst = Side(0, 0, 0, 0, n), Side(1, 0, 0, t, b * t)            # RUA_CAT -> RUA_LEFT
     fill = bytes(torch.tensor([fill_value], dtype=data.dtype).view(torch.uint8).tolist())
     row_bytes = data[0].numel() * data.element_size()

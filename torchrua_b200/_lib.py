@@ -21,7 +21,7 @@ SUM, MEAN, PROD, MAX, MIN, LOGSUMEXP = 0, 1, 2, 3, 4, 5
 
 class Ragged(Structure):
     _fields_ = [('B', c_int64), ('off', c_void_p), ('poff', c_void_p), ('sorted', c_void_p),
-                ('unsorted', c_void_p), ('Tp', c_int64), ('rank_meta', c_void_p)]
+                ('unsorted', c_void_p), ('Tp', c_int64)]
 
 
 class Side(Structure):
@@ -49,7 +49,6 @@ SIGNATURES = {
     'rua_segment_reduce_gather': (c_int32, [c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int64, c_int32, c_int32,
                                             c_void_p, c_void_p, c_size_t, c_void_p]),
     'rua_invert_permutation': (c_int32, [c_void_p, c_int64, c_void_p, c_void_p]),
-    'rua_rank_meta': (c_int32, [c_void_p, c_void_p, c_int64, c_void_p, c_void_p]),
     'rua_batch_sizes': (c_int32, [c_void_p, c_void_p, c_int64, c_int64, c_void_p, c_void_p]),
     'rua_lengths_from_pack': (c_int32, [c_void_p, c_void_p, c_int64, c_int64, c_void_p, c_void_p]),
     'rua_meta_fused_max_batch': (c_int64, []),

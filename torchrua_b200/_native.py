@@ -255,7 +255,6 @@ class Ragged:
     poff: Optional[Tensor] = None     # (Tp+1,)
     bs_cpu: Optional[Tensor] = None
     Tp: int = 0
-    rank_meta: Optional[Tensor] = None   # (2B,) see ensure_rank_meta
     _keep: list = field(default_factory=list)
     _spec_ok: bool = False            # the speculative early launch of _ensure_pack_fused held
     _stream: Optional[int] = None     # the stream the producer kernels were enqueued on (see _cache_get)
@@ -286,18 +285,7 @@ class Ragged:
         return self._T
 
     def c_struct(self) -> _lib.Ragged:
-        return _lib.Ragged(self.B, _ptr(self.off), _ptr(self.poff), _ptr(self.sorted), _ptr(self.unsorted), self.Tp,
-                           _ptr(self.rank_meta))
-
-    def ensure_rank_meta(self) -> 'Ragged':
-        """(off[sorted[r]], len[sorted[r]]) per rank: shortens the load chain of the narrow-row ragged transposes."""
-        if self.rank_meta is None and self.sorted is not None and self.B > 0:
-            lib = _lib.load()
-            with _on(self.device):
-                self.rank_meta = torch.empty(2 * self.B, dtype=torch.long, device=self.device)
-                _lib.check(lib.rua_rank_meta(self.off.data_ptr(), self.sorted.data_ptr(), self.B,
-                                             self.rank_meta.data_ptr(), _stream()), 'rua_rank_meta')
-        return self
+        return _lib.Ragged(self.B, _ptr(self.off), _ptr(self.poff), _ptr(self.sorted), _ptr(self.unsorted), self.Tp)
 
     def ensure_pack(self) -> 'Ragged':
         """add (sorted, unsorted, batch_sizes, poff) for a lengths-based batch: device radix sort (stable
@@ -546,8 +534,6 @@ def _row_map_raw(src: Tensor, spec: MapSpec, fill: bytes, feat: Tuple[int, ...],
     row_bytes = out.element_size()
     for f in feat:
         row_bytes *= f
-    if row_bytes <= 16 and (spec.src.layout == PACK) != (spec.dst.layout == PACK) and spec.rg.B >= 4096:
-        spec.rg.ensure_rank_meta()     # ragged transpose of one-vector rows: one table load instead of a dependent chain
     rg = spec.rg.c_struct()
     s, d = spec.src.c_struct(), spec.dst.c_struct()
     with _on(device):

@@ -384,16 +384,6 @@ __global__ void lengths_from_pack_kernel(const int64_t* __restrict__ bs, const i
   len[i] = lo;
 }
 
-// rank_meta[r] = (off[sorted[r]], len[sorted[r]])
-__global__ void rank_meta_kernel(const int64_t* __restrict__ off, const int64_t* __restrict__ sorted, int64_t B,
-                                 longlong2* __restrict__ out) {
-  const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (r >= B) return;
-  const int64_t i = __ldg(sorted + r);
-  const int64_t o = __ldg(off + i);
-  out[r] = make_longlong2(o, __ldg(off + i + 1) - o);
-}
-
 // off[m] = first rank r with keys[sorted[r]] >= m  (keys o sorted is non-decreasing), m in [0, M]
 __global__ void bucket_offsets_kernel(const int64_t* __restrict__ keys, const int64_t* __restrict__ sorted,
                                       int64_t n, int64_t M, int64_t* __restrict__ off) {
@@ -554,14 +544,6 @@ int rua_bucket_offsets(const int64_t* keys, const int64_t* sorted, int64_t n, in
   if (n < 0 || M < 0 || !off) return RUA_ERR_INVALID;
   if (n > 0 && (!keys || !sorted)) return RUA_ERR_INVALID;
   bucket_offsets_kernel<<<(unsigned)ceil_div(M + 1, 256), 256, 0, (cudaStream_t)stream>>>(keys, sorted, n, M, off);
-  return check_launch();
-}
-
-int rua_rank_meta(const int64_t* off, const int64_t* sorted, int64_t B, int64_t* rank_meta, rua_stream_t stream) {
-  if (B < 0) return RUA_ERR_INVALID;
-  if (B == 0) return RUA_OK;
-  if (!off || !sorted || !rank_meta || ((uintptr_t)rank_meta & 15u)) return RUA_ERR_INVALID;
-  rank_meta_kernel<<<(unsigned)ceil_div(B, 256), 256, 0, (cudaStream_t)stream>>>(off, sorted, B, (longlong2*)rank_meta);
   return check_launch();
 }
 

@@ -116,12 +116,10 @@ segreduce_kernel(const T* __restrict__ data, const int64_t* __restrict__ ridx, c
           // max and the global-extreme tracking run on packed pairs (HMNMX2), halving their issue cost.
           if (active) lse_batch<T, V, kRedUnroll>(raw, st.a, st.s, ext, ext2);
           done = true;
-        } else if (V > 1) {
-          // a segment boundary inside the batch: the same batched form on the rows [k, e) only (the boundary is
-          // uniform across the CTA), instead of one online update -- exp, rescale, selects -- per element
-          if (active) lse_batch_range<T, V, kRedUnroll>(raw, k, e, st.a, st.s, ext, ext2);
-          done = true;
         }
+        // (round 2: a masked batched form for boundary batches -- rows [k, e) only -- measured 81.3 % of peak at cfg3
+        // against 84.6 % for the per-element update below: the kernel sits at its 80-register cap and the extra code
+        // costs more than the ~13 % of rows it would speed up.  Dropped.)
       }
       if (!done && active) {
 #pragma unroll

@@ -304,85 +304,6 @@ __device__ __forceinline__ void lse_batch(const Raw<T, V>* raw, typename Store<T
 }
 
 
-// the same for the rows [lo, hi) of a batch only (a segment boundary falls inside the batch): every row keeps its static
-// register index, rows outside the range are predicated off.  Replaces the per-element online update (one exp, two
-// selects and a rescale per element) that boundary batches used to fall back to.
-template <typename T, int V, int kRows>
-__device__ __forceinline__ void lse_batch_range(const Raw<T, V>* raw, int lo, int hi, typename Store<T>::Acc* a,
-                                                typename Store<T>::Acc* s, typename Store<T>::Acc& ext, uint32_t* ext2) {
-  using A = typename Store<T>::Acc;
-  A bm[V];
-  if constexpr (Pk<T>::kHas && V == 8) {
-    constexpr uint32_t kNegInf = Pk<T>::kPosInf | 0x80008000u;
-    uint32_t m2[4] = {kNegInf, kNegInf, kNegInf, kNegInf};
-#pragma unroll
-    for (int k = 0; k < kRows; ++k) {
-      if (k >= lo && k < hi) {
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const uint32_t w = word_of(raw[k].r, j);
-          m2[j] = Pk<T>::max_nan(m2[j], w);
-          ext2[j] = Pk<T>::min_num(ext2[j], w);
-        }
-      }
-    }
-#pragma unroll
-    for (int j = 0; j < 4; ++j) Pk<T>::unpack(m2[j], bm[2 * j], bm[2 * j + 1]);
-  } else {
-#pragma unroll
-    for (int v = 0; v < V; ++v) bm[v] = -inf_of<A>();
-#pragma unroll
-    for (int k = 0; k < kRows; ++k) {
-      if (k >= lo && k < hi) {
-        A x[V];
-        unpack_raw<T, V>(raw[k], x);
-#pragma unroll
-        for (int v = 0; v < V; ++v) {
-          bm[v] = max_nan(bm[v], x[v]);
-          ext = min_num(ext, x[v]);
-        }
-      }
-    }
-  }
-  if constexpr (sizeof(A) == 4) {
-    constexpr float kLog2e = 1.4426950408889634f;
-    float mb[V];
-#pragma unroll
-    for (int v = 0; v < V; ++v) {
-      float m_new = max_nan(a[v], bm[v]);
-      s[v] = s[v] == 0.f ? 0.f : s[v] * ex2_approx((a[v] - m_new) * kLog2e);
-      a[v] = m_new;
-      mb[v] = m_new * kLog2e;
-    }
-#pragma unroll
-    for (int k = 0; k < kRows; ++k) {
-      if (k >= lo && k < hi) {
-        A x[V];
-        unpack_raw<T, V>(raw[k], x);
-#pragma unroll
-        for (int v = 0; v < V; ++v) s[v] += ex2_approx(fmaf(x[v], kLog2e, -mb[v]));
-      }
-    }
-  } else {
-#pragma unroll
-    for (int v = 0; v < V; ++v) {
-      A m_new = max_nan(a[v], bm[v]);
-      s[v] = s[v] == A(0) ? A(0) : s[v] * exp(a[v] - m_new);
-      a[v] = m_new;
-    }
-#pragma unroll
-    for (int k = 0; k < kRows; ++k) {
-      if (k >= lo && k < hi) {
-        A x[V];
-        unpack_raw<T, V>(raw[k], x);
-#pragma unroll
-        for (int v = 0; v < V; ++v) s[v] += exp(x[v] - a[v]);
-      }
-    }
-  }
-}
-
-
 // ---------------------------------------------------------------------------------------------
 // per-op accumulator state shared by the wide-row kernel (reduce.cu) and the flat kernel (reduce_flat.cu)
 // ---------------------------------------------------------------------------------------------

@@ -1033,21 +1033,24 @@ row_map_transpose_kernel(const RowMapParams p, const int TT_) {
 }
 
 // The same ragged transpose for ONE-VECTOR rows (token ids, per-token scalars: BASELINE config 5), restructured around
-// what bounds it: latency.  ncu on the one-tile-per-CTA kernel (8-byte rows): long-scoreboard stalls dominate, 42 % DRAM,
-// 59 % warps active -- a CTA spends most of its ~2 us life NOT having loads in flight (metadata chain, shared-memory
-// hop, barrier, stores, launch / retire), and shortening the chain alone (rank_meta) did not move it.  So the CTAs are
-// PERSISTENT and software-pipelined: while tile k is written out of shared memory, the row loads of tile k+1 are already
-// in flight in registers and the metadata of tile k+2 is on its way; a tile = 32 ranks x KT time-tiles of 32 steps.
-struct T1Meta {          // what one warp needs to know about its slice of a tile
-  int64_t pt, bst;       // lane kt * 4 + k: poff / batch size of time step (kt * 32 + warp + 8 k)
-  int64_t i, o, len;     // lane k: sequence, first C row, length of rank (warp + 8 k)
-};
-
+// what bounds it: latency.  ncu on the kernel above (8-byte rows): 94 % warps active, 36 % DRAM -- a CTA lives ~4 us for
+// 8 KB in + 8 KB out because its loads form a chain (poff[t] -> rows of P; sorted[r] -> off[i] -> rows of C) and the
+// second chain only started after the barrier.  Here (1) BOTH metadata chains are started at kernel entry, and (2) a CTA
+// owns KT time-tiles of 32 steps for its 32 ranks and issues the row loads of all of them before the first shared-
+// memory store, so the chain is paid once per KT * 8 KB and KT times as many bytes are in flight per thread.
+// Round-2 record (profiles/r2_transpose.md): this form reaches 46-48 % (C -> P) / 40 % (P -> C) of the HBM peak on 8-byte rows.
+// Two further restructurings were measured and dropped: a per-rank (offset, length) table that turns the chain into
+// one coalesced load (no change), and PERSISTENT software-pipelined CTAs that keep the next tile's loads in flight while
+// the current one is stored (40 % / 34 %: worse).  ncu shows why: the kernel moves 586 MB of DRAM traffic for 528 MB
+// of payload (64-byte DRAM granules around 256-byte runs that start at arbitrary offsets) at 3.4 TB/s -- the runs
+// belong to sequences in SORTED order, i.e. scattered over the whole C buffer, and that access pattern, not latency
+// hiding, is the ceiling.
 template <typename V, bool kFromPack, int KT>
-__global__ void __launch_bounds__(256, KT == 4 ? 2 : 3)
-row_map_transpose1_kernel(const RowMapParams p, const int64_t tiles_t, const int64_t total_tiles) {
+__global__ void __launch_bounds__(256, KT == 1 ? 8 : (KT == 2 ? 5 : 4))
+row_map_transpose1_kernel(const RowMapParams p) {
   __shared__ V tile[KT][32][33];                     // [time tile][time step][rank] (+1: bank skew)
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int64_t r0 = (int64_t)blockIdx.x * 32, t0 = (int64_t)blockIdx.y * (32 * KT);
   const rua_side_t& sq = kFromPack ? p.d : p.s;     // the sequence-major side
   const int64_t B = p.rg.B, Tp = p.rg.Tp, W = sq.width;
   const int64_t* __restrict__ poff = p.rg.poff;
@@ -1056,111 +1059,88 @@ row_map_transpose1_kernel(const RowMapParams p, const int64_t tiles_t, const int
   const V* __restrict__ src = reinterpret_cast<const V*>(p.src);
   V* __restrict__ dst = reinterpret_cast<V*>(p.dst);
 
-  auto fetch_meta = [&](int64_t id, T1Meta& m) {      // issues the loads; nothing waits on them here
-    m.pt = m.bst = m.i = m.o = m.len = 0;
-    if (id >= total_tiles) return;
-    const int64_t r0 = (id / tiles_t) * 32, t0 = (id % tiles_t) * (32 * KT);
-    if (lane < 4 * KT) {
-      const int64_t t = t0 + (lane >> 2) * 32 + warp + 8 * (lane & 3);
-      if (t < Tp) { m.pt = __ldg(poff + t); m.bst = __ldg(poff + t + 1) - m.pt; }
+  // ---- both metadata chains start now ---------------------------------------------------------------------------
+  // pack side: this warp's time steps are tt = warp + 8 k of every time tile; lane (kt * 4 + k) fetches poff for it
+  int64_t my_pt = 0, my_bst = 0;
+  if (lane < 4 * KT) {
+    const int64_t t = t0 + (lane >> 2) * 32 + warp + 8 * (lane & 3);
+    if (t < Tp) { my_pt = __ldg(poff + t); my_bst = __ldg(poff + t + 1) - my_pt; }
+  }
+  // sequence side: this warp's ranks are r0 + warp + 8 k; lane k fetches sorted -> off for it
+  int64_t my_i = 0, my_o = 0, my_len = 0;
+  if (lane < 4) {
+    const int64_t r = r0 + warp + 8 * lane;
+    if (r < B) {
+      my_i = __ldg(p.rg.sorted + r);
+      my_o = __ldg(off + my_i);
+      my_len = __ldg(off + my_i + 1) - my_o;
     }
-    if (lane < 4) {
-      const int64_t r = r0 + warp + 8 * lane;
-      if (r < B) {
-        m.i = __ldg(p.rg.sorted + r);
-        if (p.rg.rank_meta) {                          // one coalesced 16-byte load instead of the chain sorted -> off
-          const longlong2 q = __ldg(reinterpret_cast<const longlong2*>(p.rg.rank_meta) + r);
-          m.o = q.x;
-          m.len = q.y;
-        } else {
-          m.o = __ldg(off + m.i);
-          m.len = __ldg(off + m.i + 1) - m.o;
-        }
-      }
-    }
-  };
+  }
+  // no token of this CTA exists when the batch size at its first time step does not reach its first rank
+  {
+    const int64_t bs0 = t0 < Tp ? __ldg(poff + t0 + 1) - __ldg(poff + t0) : 0;
+    if (!padded_dst && bs0 <= r0) return;           // CTA-uniform
+  }
   auto seq_row = [&](int64_t i, int64_t o, int64_t len, int64_t t) -> int64_t {
     return sq.layout == RUA_CAT ? o + t : (sq.layout == RUA_LEFT ? i * W + t : i * W + (W - len) + t);
   };
+
   V val[KT][4];
   unsigned on = 0;                                   // bit kt * 4 + k: val[kt][k] holds a row
-  auto issue_loads = [&](int64_t id, const T1Meta& m) {
-    on = 0;
-    if (id >= total_tiles) return;
-    const int64_t r0 = (id / tiles_t) * 32, t0 = (id % tiles_t) * (32 * KT);
-    if (kFromPack) {                                 // read P along ranks
+  if (kFromPack) {   // ---- P -> C / L: read P along ranks ----------------------------------------------------------
 #pragma unroll
-      for (int kt = 0; kt < KT; ++kt)
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          const int64_t pt = shfl_i64(m.pt, kt * 4 + k), bst = shfl_i64(m.bst, kt * 4 + k);
-          if (r0 + lane < bst) {                     // bst == 0 beyond Tp
-            on |= 1u << (kt * 4 + k);
-            val[kt][k] = ld_stream(src + pt + r0 + lane);
-          }
-        }
-    } else {                                         // read the sequence-major side along time
+    for (int kt = 0; kt < KT; ++kt)
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
-        const int64_t i = shfl_i64(m.i, k), o = shfl_i64(m.o, k), len = shfl_i64(m.len, k);
-#pragma unroll
-        for (int kt = 0; kt < KT; ++kt) {
-          const int64_t t = t0 + kt * 32 + lane;
-          if (r0 + warp + 8 * k < B && t < len) {
-            on |= 1u << (kt * 4 + k);
-            val[kt][k] = ld_stream(src + seq_row(i, o, len, t));
-          }
+        const int64_t pt = shfl_i64(my_pt, kt * 4 + k), bst = shfl_i64(my_bst, kt * 4 + k);
+        if (r0 + lane < bst) {                       // bst == 0 beyond Tp
+          on |= 1u << (kt * 4 + k);
+          val[kt][k] = ld_stream(src + pt + r0 + lane);
         }
       }
-    }
-  };
-
-  int64_t id = blockIdx.x;
-  T1Meta cur, nxt;
-  fetch_meta(id, cur);
-  fetch_meta(id + gridDim.x, nxt);
-  issue_loads(id, cur);
-  for (; id < total_tiles; id += gridDim.x) {
-    const int64_t r0 = (id / tiles_t) * 32, t0 = (id % tiles_t) * (32 * KT);
-    // ---- tile `id` has arrived in registers: through shared memory, transposed -------------------------------------
 #pragma unroll
     for (int kt = 0; kt < KT; ++kt)
 #pragma unroll
       for (int k = 0; k < 4; ++k)
-        if (on >> (kt * 4 + k) & 1u) {
-          if (kFromPack) tile[kt][warp + 8 * k][lane] = val[kt][k];
-          else tile[kt][lane][warp + 8 * k] = val[kt][k];
-        }
+        if (on >> (kt * 4 + k) & 1u) tile[kt][warp + 8 * k][lane] = val[kt][k];
     __syncthreads();
-    // ---- the next tile's rows go in flight, and the metadata of the one after that ----------------------------------
-    issue_loads(id + gridDim.x, nxt);
-    T1Meta after;
-    fetch_meta(id + 2 * (int64_t)gridDim.x, after);
-    // ---- write tile `id` --------------------------------------------------------------------------------------------
-    if (kFromPack) {
 #pragma unroll
-      for (int k = 0; k < 4; ++k) {                  // the sequence-major side, along time
-        const int64_t i = shfl_i64(cur.i, k), o = shfl_i64(cur.o, k), len = shfl_i64(cur.len, k);
-        if (r0 + warp + 8 * k >= B) break;           // warp-uniform
+    for (int k = 0; k < 4; ++k) {                    // write the sequence-major side along time
+      const int64_t i = shfl_i64(my_i, k), o = shfl_i64(my_o, k), len = shfl_i64(my_len, k);
+      if (r0 + warp + 8 * k >= B) break;             // warp-uniform
 #pragma unroll
-        for (int kt = 0; kt < KT; ++kt) {
-          const int64_t t = t0 + kt * 32 + lane;
-          if (t < len) st_stream(dst + seq_row(i, o, len, t), tile[kt][lane][warp + 8 * k]);
-          else if (padded_dst && t < W) st_stream(dst + i * W + t, make_fill<V>(p.fill, 0));   // left-aligned padding
+      for (int kt = 0; kt < KT; ++kt) {
+        const int64_t t = t0 + kt * 32 + lane;
+        if (t < len) st_stream(dst + seq_row(i, o, len, t), tile[kt][lane][warp + 8 * k]);
+        else if (padded_dst && t < W) st_stream(dst + i * W + t, make_fill<V>(p.fill, 0));   // left-aligned padding
+      }
+    }
+  } else {           // ---- C / L / R -> P: read the sequence-major side along time ---------------------------------
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int64_t i = shfl_i64(my_i, k), o = shfl_i64(my_o, k), len = shfl_i64(my_len, k);
+#pragma unroll
+      for (int kt = 0; kt < KT; ++kt) {
+        const int64_t t = t0 + kt * 32 + lane;
+        if (r0 + warp + 8 * k < B && t < len) {
+          on |= 1u << (kt * 4 + k);
+          val[kt][k] = ld_stream(src + seq_row(i, o, len, t));
         }
       }
-    } else {
-#pragma unroll
-      for (int kt = 0; kt < KT; ++kt)
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          const int64_t pt = shfl_i64(cur.pt, kt * 4 + k), bst = shfl_i64(cur.bst, kt * 4 + k);
-          if (r0 + lane < bst) st_stream(dst + pt + r0 + lane, tile[kt][warp + 8 * k][lane]);
-        }
     }
-    __syncthreads();                                 // the tile buffer is free again
-    cur = nxt;
-    nxt = after;
+#pragma unroll
+    for (int kt = 0; kt < KT; ++kt)
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+        if (on >> (kt * 4 + k) & 1u) tile[kt][lane][warp + 8 * k] = val[kt][k];
+    __syncthreads();
+#pragma unroll
+    for (int kt = 0; kt < KT; ++kt)
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int64_t pt = shfl_i64(my_pt, kt * 4 + k), bst = shfl_i64(my_bst, kt * 4 + k);
+        if (r0 + lane < bst) st_stream(dst + pt + r0 + lane, tile[kt][warp + 8 * k][lane]);
+      }
   }
 }
 
@@ -1193,12 +1173,8 @@ static void launch_narrow(RowMapParams& p, int64_t rows, cudaStream_t st) {
       // one-vector rows: KT time tiles of 32 steps per CTA, all of their row loads in flight together
       constexpr int kMaxKT = sizeof(V) >= 16 ? 2 : 4;   // 48 KB of static shared memory
       const int kt = gy <= 1 ? 1 : ((gy <= 2 || kMaxKT == 2) ? 2 : 4);
-      const int64_t tiles_t = ceil_div(gy, kt), total = ceil_div(p.rg.B, 32) * tiles_t;
-      // persistent CTAs (3 per SM, 2 with the largest tile: the pipeline keeps three tiles of state in registers), each
-      // walking tiles blockIdx.x, + gridDim.x, ...
-      const int64_t resident = (int64_t)kNumSMs * (kt == 4 ? 2 : 3);
-      const unsigned g1 = (unsigned)(total < resident ? total : resident);
-#define RUA_T1(FP_, KT_) row_map_transpose1_kernel<V, FP_, KT_><<<g1, 256, 0, st>>>(p, tiles_t, total)
+      dim3 g1((unsigned)ceil_div(p.rg.B, 32), (unsigned)ceil_div(gy, kt));
+#define RUA_T1(FP_, KT_) row_map_transpose1_kernel<V, FP_, KT_><<<g1, 256, 0, st>>>(p)
       if (from_pack) { if (kt == 1) RUA_T1(true, 1); else if (kt == 2) RUA_T1(true, 2); else RUA_T1(true, kMaxKT); }
       else { if (kt == 1) RUA_T1(false, 1); else if (kt == 2) RUA_T1(false, 2); else RUA_T1(false, kMaxKT); }
 #undef RUA_T1

@@ -660,7 +660,7 @@ def time_output_gather(args, step, data, lens, lens_host, glens, parts, rank, wo
             cuts.append((start, end, int(csum[start - 1]) if start else 0, int(csum[end - 1])))
         start = end
     ids_local = parts[rank].to(dev)
-    side = torch.cuda.Stream(dev)
+    side = torch.cuda.Stream(dev, priority=-1)        # the wire-bound gather gets CTA slots as soon as they free up
 
     def fused_step():
         _native._CACHE.clear()
@@ -668,16 +668,7 @@ def time_output_gather(args, step, data, lens, lens_host, glens, parts, rank, wo
         windows.fence()                                   # peers have finished reading last step's window
         goff, _ = _native.scan(glens_dev)                 # where every sequence of the GLOBAL batch starts
         back = torch.empty((n_local, HIDDEN), dtype=data.dtype, device=dev)
-        s = torch.empty((lens_host.numel(), HIDDEN), dtype=data.dtype, device=dev)
-        m = torch.empty_like(s)
-        keep, landed = [], []
-
-        def reduce_part(j):
-            a, b, ta, tb = cuts[j]
-            cur.wait_event(landed[j])                     # the local copy of micro-batch j has been written
-            s[a:b] = rua.segment_sum(back[ta:tb], lens[a:b])
-            m[a:b] = rua.segment_max(back[ta:tb], lens[a:b])
-
+        keep = []
         for k, (a, b, ta, tb) in enumerate(cuts):
             right = rua.C(data=data[ta:tb], token_sizes=lens[a:b]).pack().left(0).right(0)
             ready = torch.cuda.Event()
@@ -686,14 +677,12 @@ def time_output_gather(args, step, data, lens, lens_host, glens, parts, rank, wo
                 side.wait_event(ready)
                 shard.gather_catted_fused(right, parts, glens_dev, windows, fence=False, seq_ids=ids_local[a:b],
                                           goff=(goff, total_tokens), local_out=back[ta:tb])
-                ev = torch.cuda.Event()
-                ev.record(side)
-            landed.append(ev)
             keep.append(right)                            # allocated on `cur`, read on `side`: freed after the join below
-            if k > 0:
-                reduce_part(k - 1)
-        reduce_part(len(cuts) - 1)
         cur.wait_stream(side)
+        # the reductions run on the WHOLE local copy, exactly like the single-GPU step: bit-identical results (reducing
+        # micro-batch slices would move the chunk boundaries of the fp32 accumulation)
+        s = rua.segment_sum(back, lens)
+        m = rua.segment_max(back, lens)
         full = windows.view((total_tokens, HIDDEN), data.dtype, 0)
         gs = shard.gather_rows_fused(s, parts, windows, offset_bytes=sum_off, fence=False)
         gm = shard.gather_rows_fused(m, parts, windows, offset_bytes=max_off, fence=False)
@@ -734,7 +723,8 @@ def time_output_gather(args, step, data, lens, lens_host, glens, parts, rank, wo
                                 'micro_batches': len(cuts),
                                 'ingress_floor_ms_at_900GBs': wire / 900e9 * 1e3,
                                 'how': 'per micro-batch: conversions on the main stream, fused R->C + NVLink peer stores on a '
-                                       'side stream, reductions as soon as the local copy has landed'},
+                                       'high-priority side stream with a capped grid (4 CTAs / SM), so the HBM-bound conversions of '
+                                       'the next micro-batch share the SMs with the wire-bound stores'},
            'nccl_all_gather_then_permute': {'ms_per_step': n_ms, 'value': total_tokens / (n_ms * 1e-3),
                                             'unit': 'tokens/s'},
            'results_identical': same, 'steps': steps,

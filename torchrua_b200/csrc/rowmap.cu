@@ -437,15 +437,18 @@ struct MultiDst {
   int32_t rows_are_sequences;
 };
 
+// The grid may be CAPPED (launch_row_map_multi): with many destinations the kernel is bound by the NVLink wire, not by
+// SM issue, so a few CTAs per SM walk the rows in a grid-stride loop and leave the remaining CTA slots of every SM to
+// the HBM-bound conversions of the next micro-batch running on another stream (true overlap instead of time slicing).
 template <typename V>
 __global__ void __launch_bounds__(kRowMapThreads)
 row_map_multi_kernel(const RowMapParams p, const MultiDst m) {
   const int lane = threadIdx.x & 31;
-  const int64_t warp = (int64_t)blockIdx.x * (kRowMapThreads / 32) + (threadIdx.x >> 5);
   const int rpw = p.rows_per_warp;
   const int64_t rows = p.d.rows;
+  const int64_t warps_total = (int64_t)gridDim.x * (kRowMapThreads / 32);
+  for (int64_t warp = (int64_t)blockIdx.x * (kRowMapThreads / 32) + (threadIdx.x >> 5); warp * rpw < rows; warp += warps_total) {
   const int64_t j0 = warp * rpw;
-  if (j0 >= rows) return;
 
   int64_t srow = kNoRow, seq = 0, tok = 0;
   {
@@ -503,6 +506,7 @@ row_map_multi_kernel(const RowMapParams p, const MultiDst m) {
       }
     }
   }
+  }   // grid-stride loop over the warps' row groups
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1358,7 +1362,11 @@ static int launch_row_map_multi(RowMapParams& p, const MultiDst& m, int64_t row_
   int splits = 1;
   while (warps * splits < target_warps && p.row_vecs / (splits * 2) >= 32 * kUnroll && splits < 64) splits *= 2;
   p.col_splits = splits;
-  const int64_t blocks = ceil_div(warps, kRowMapThreads / 32);
+  int64_t blocks = ceil_div(warps, kRowMapThreads / 32);
+  // wire-bound (>= 4 destinations, i.e. >= 2 peers beside the local window and copy): cap the grid so that other streams'
+  // kernels find free CTA slots on every SM; RUA_MULTI_CTAS_PER_SM overrides (0 = no cap)
+  static const int cap_per_sm = [] { const char* e = getenv("RUA_MULTI_CTAS_PER_SM"); return e ? atoi(e) : 4; }();
+  if (m.n >= 4 && cap_per_sm > 0 && blocks > (int64_t)kNumSMs * cap_per_sm) blocks = (int64_t)kNumSMs * cap_per_sm;
   if (blocks >= (1ll << 31)) return RUA_ERR_UNSUPPORTED;
   dim3 grid((unsigned)blocks, (unsigned)splits);
   switch (vec) {

@@ -486,6 +486,14 @@ def run_ours(args):
         kernels['segment_reduce'] = {'gbs': sr[1] / (sr[0] * 1e-3) / 1e9, 'ms_per_launch': sr[0] / sr[2],
                                      'launches': sr[2], 'share_of_step': sr[0] / ms_total}
 
+    if args.gather_only:     # diagnostic: only the output-gather leg (fused path), one short JSON line
+        g = time_output_gather(args, step, data, lens, lens_host, glens, parts, rank, world, dev, total_tokens, barrier)
+        if rank == 0:
+            emit({'gather_only': g, 'n_gpus': world, 'ms_per_step_no_gather': ms_total / args.steps,
+                  'env': {k: v for k, v in os.environ.items() if k.startswith('RUA_')}})
+        dist.destroy_process_group()
+        return
+
     # ---- end to end through the public API with HOST buffers (H2D + D2H inside the timed region) --
     e2e_steps = max(4, min(args.steps, 20))     # pipeline fill and drain (one un-overlapped copy each way) are inside the timed region
     h_data = torch.empty((n_tok, HIDDEN), dtype=torch.bfloat16, pin_memory=True)
@@ -712,6 +720,9 @@ def time_output_gather(args, step, data, lens, lens_host, glens, parts, rank, wo
         return out, float(ms) / steps
 
     (f_full, f_s, f_m), f_ms = timed(fused_step)
+    if args.gather_only:
+        windows.close()
+        return {'fused_ms_per_step': f_ms, 'micro_batches': len(cuts), 'nvlink_out_GBs_per_rank': (world - 1) * int(lens_host.sum()) * row / (f_ms * 1e-3) / 1e9}
     (n_full, n_s, n_m), n_ms = timed(nccl_step)
     same = bool(torch.equal(f_full, n_full) and torch.equal(f_s, n_s) and torch.equal(f_m, n_m))
     # the global C data restricted to this rank's sequences is this rank's input (round trip = identity)
@@ -771,6 +782,7 @@ def main():
     ap.add_argument('--ref-seqs', type=int, default=0, help='reference arm: sequences per step (0 = full batch if it fits the budget)')
     ap.add_argument('--ref-budget', type=float, default=200.0, help='reference arm: seconds for the whole run')
     ap.add_argument('--no-gather', action='store_true', help='skip the output-gather legs of multi-GPU runs')
+    ap.add_argument('--gather-only', action='store_true', help='diagnostic: time only the fused output-gather leg (N > 1)')
     ap.add_argument('--gather-micro-batches', type=int, default=4,
                     help='output gather: micro-batches per step (peer stores of one overlap the conversions of the next)')
     ap.add_argument('--exchange', default='peer', choices=['peer', 'nccl', 'none'],

@@ -199,7 +199,7 @@ def scan(sizes: Optional[Tensor], clamp_max: int = INT64_MAX, notify: bool = Fal
     else:
         bs_dev, unsorted, tp, n = pack
         dev = unsorted.device
-    tiles = (n + 4095) // 4096 + 1          # == rua_scan_workspace_bytes(n) / 8
+    tiles = (n + 1023) // 1024 + 1          # >= rua_scan_workspace_bytes(n) / 8 (1024 lengths per CTA above 4096)
     note = None
     with _on(dev):
         # one allocation: [off (n+1) | stats (2) | tile status words + completion counter (tiles) | lengths (n, pack only)]

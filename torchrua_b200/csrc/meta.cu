@@ -21,8 +21,11 @@ long long g_launch_count = 0;
 // exclusive scan + max
 // ------------------------------------------------------------------------------------------------
 constexpr int kScanThreads = 256;
-constexpr int kScanItems = 16;
-constexpr int kScanTile = kScanThreads * kScanItems;  // 2048
+constexpr int kScanItemsOne = 16;                          // up to 4096 lengths: ONE CTA, no look-back, no memset
+constexpr int kScanItemsMany = 4;                          // larger vectors: 1024 per CTA -- B = 1 M is 977 CTAs instead of
+                                                           // 245 (1.65 CTAs per SM: the chained scan was latency-bound)
+constexpr int kScanTileOne = kScanThreads * kScanItemsOne;
+constexpr int kScanTileMany = kScanThreads * kScanItemsMany;
 
 __device__ __forceinline__ int64_t warp_incl_scan(int64_t v, int lane) {
 #pragma unroll
@@ -71,9 +74,11 @@ struct ScanExtras {
   int64_t tiles;
 };
 
+template <int kScanItems>
 __global__ void __launch_bounds__(kScanThreads)
 scan_kernel(const int64_t* __restrict__ in, int64_t n, int64_t clamp_max, int64_t* __restrict__ out,
             int64_t* __restrict__ stats, unsigned long long* status, int multi_tile, const ScanExtras ex) {
+  constexpr int kScanTile = kScanThreads * kScanItems;
   __shared__ int64_t s_warp[kScanThreads / 32];
   __shared__ int64_t s_wmax[kScanThreads / 32];
   __shared__ int64_t s_prefix;
@@ -420,7 +425,7 @@ int rua_last_cuda_error(void) { return g_last_cuda_error; }
 int64_t rua_launch_count(void) { return (int64_t)g_launch_count; }
 
 size_t rua_scan_workspace_bytes(int64_t n) {
-  int64_t tiles = n > 0 ? ceil_div(n, kScanTile) : 1;
+  int64_t tiles = n > kScanTileOne ? ceil_div(n, kScanTileMany) : 1;
   return (size_t)(tiles + 1) * sizeof(unsigned long long);   // tile status words + the completion counter
 }
 
@@ -441,7 +446,7 @@ int rua_scan_lengths_ex(const int64_t* sizes, int64_t n, int64_t clamp_max, int6
     scan_empty_kernel<<<1, 1, 0, st>>>(off, stats, ex.notify, ticket);
     return check_launch();
   }
-  int64_t tiles = ceil_div(n, kScanTile);
+  int64_t tiles = n > kScanTileOne ? ceil_div(n, kScanTileMany) : 1;
   ex.tiles = tiles;
   int multi = tiles > 1;
   if (multi) {
@@ -458,7 +463,8 @@ int rua_scan_lengths_ex(const int64_t* sizes, int64_t n, int64_t clamp_max, int6
       if (rc) return rc;
     }
   }
-  scan_kernel<<<(unsigned)tiles, kScanThreads, 0, st>>>(sizes, n, clamp_max, off, stats, (unsigned long long*)ws, multi, ex);
+  if (multi) scan_kernel<kScanItemsMany><<<(unsigned)tiles, kScanThreads, 0, st>>>(sizes, n, clamp_max, off, stats, (unsigned long long*)ws, multi, ex);
+  else scan_kernel<kScanItemsOne><<<1, kScanThreads, 0, st>>>(sizes, n, clamp_max, off, stats, (unsigned long long*)ws, multi, ex);
   return check_launch();
 }
 

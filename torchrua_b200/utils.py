@@ -37,6 +37,9 @@ def to_self(self: Any, *_, **__) -> Any:
     return self
 
 
+# The four helpers below are NOT on the hot path (no other file of the reference uses them); they are
+# kept, with the reference's semantics (utils.py:33-51), only so that `from torchrua import *` exposes the same names --
+# tests/test_abi.py compares the public surface name by name.  Host-side shape arithmetic over torch views: no kernel.
 def with_shape(shape: torch.Size, dim: int, value: int) -> List[int]:
     out = list(shape)
     out[dim] = value

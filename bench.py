@@ -266,7 +266,28 @@ def time_reference_cuda(ref, steps: int, warmup: int, n_seq: int):
     b.record()
     torch.cuda.synchronize()
     ms = a.elapsed_time(b) / steps
-    return n_tok / (ms * 1e-3), ms, n_seq or BATCH, n_tok
+    # the same ops one by one (CUDA events around each public-API call of the reference, median of 5 after 2 warm-ups):
+    # the per-op kernel-to-beat of SURVEY.md 8d
+    lens = workload_lengths(1)[:n_seq or BATCH].to('cuda')
+    c = ref.C(data=data, token_sizes=lens)
+    p = c.pack()
+    left = p.left(0)
+    right = left.right(0)
+    ops = {'C->P': lambda: c.pack(), 'P->L': lambda: p.left(0), 'L->R': lambda: left.right(0), 'R->C': lambda: right.cat(),
+           'segment_sum': lambda: ref.segment_sum(data, lens), 'segment_max': lambda: ref.segment_max(data, lens)}
+    per_op = {}
+    for name, fn in ops.items():
+        times = []
+        for it in range(7):
+            torch.cuda.synchronize()
+            a.record()
+            fn()
+            b.record()
+            torch.cuda.synchronize()
+            if it >= 2:
+                times.append(a.elapsed_time(b))
+        per_op[name] = round(statistics.median(times), 4)
+    return n_tok / (ms * 1e-3), ms, n_seq or BATCH, n_tok, per_op
 
 
 def run_reference(args):
@@ -274,10 +295,10 @@ def run_reference(args):
     if rank != 0:
         return
     ref = import_reference()
-    port = None
+    port = ref_ops = None
     if args.ref_device == 'cuda':
         assert ref is not None, 'oracle/_ref is not staged'
-        tps, ms, n_seq, n_tok = time_reference_cuda(ref, args.steps, args.warmup, args.ref_seqs)
+        tps, ms, n_seq, n_tok, ref_ops = time_reference_cuda(ref, args.steps, args.warmup, args.ref_seqs)
         kind, threads, device = 'reference', 0, 'the same GPU (stock ATen CUDA kernels), CUDA events'
     elif ref is not None:
         tps, ms, n_seq, n_tok, threads = time_reference_cpu(ref, args.steps, max(args.warmup, 1), args.ref_budget,
@@ -309,6 +330,8 @@ def run_reference(args):
         'e2e': {'value': tps, 'unit': 'tokens/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
         'gpu_launches': 0,
     }
+    if ref_ops is not None:
+        line['per_op_ms'] = ref_ops
     emit(line)
 
 
@@ -590,7 +613,10 @@ def run_ours(args):
                         'sample': r['cpu_baseline']['sample'], 'steps': 5, 'warmup': 5,
                         'what': 'the UNMODIFIED reference (oracle/_ref) running the same step on the same B200 through '
                                 'its stock ATen CUDA path, CUDA events, separate process',
-                        'speedup_of_value': value / r['value']}
+                        'speedup_of_value': value / r['value'],
+                        'per_op_ms': r.get('per_op_ms'),
+                        'ours_per_launch_ms': {'row_map (mean of C->P, P->L, L->R, R->C)': rm[0] / max(rm[2], 1),
+                                               'segment_reduce (mean of sum, max)': (sr[0] / sr[2]) if sr else None}}
         r = reference_subprocess(['--steps', '3', '--warmup', '1', '--ref-seqs', '512'], timeout_s=300)
         if 'unavailable' in r:
             cpu = None

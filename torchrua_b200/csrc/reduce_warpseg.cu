@@ -17,6 +17,9 @@
 //     tree), so a long sequence among short ones costs bandwidth, not a serial loop;
 //   * every segment is finished by the lane that owns it: no cross-tile pieces, no span kernel, results stored coalesced.
 // The launcher picks this kernel when there are enough segments to fill the machine (reduce.cu: plan_reduce).
+// Measured and dropped (round 2): 256-thread CTAs (4.4 waves at cfg5: 51 % vs 55 % of peak for 128 threads), and TWO groups of 32
+// segments per warp with both first windows in flight (43 %: the extra state costs occupancy, which is what hides the two serial
+// DRAM latencies -- offsets, then the window -- of a warp).
 #include <cstdlib>
 
 #include "reduce_common.cuh"

@@ -26,8 +26,21 @@ def side_of(self: Z, rg: '_native.Ragged') -> SideSpec:
     return SideSpec(RIGHT if isinstance(self, R) else LEFT, width=w, rows=b * w)
 
 
+def _check_source(src: SideSpec, rg: '_native.Ragged') -> None:
+    """host-only consistency check of the metadata against the storage, whenever N / T are already known on the host
+    (they are after the first conversion of a batch): lengths that describe more tokens than the storage holds would
+    make the kernels read past the payload (the reference's advanced indexing raises an IndexError there)."""
+    if src.layout in (CAT, PACK):
+        if rg._N is not None and rg._N > src.rows:
+            raise IndexError(f'torchrua_b200: token_sizes describe {rg._N} tokens but data holds {src.rows} rows')
+    elif rg._T is not None and rg._T > src.width:
+        raise IndexError(f'torchrua_b200: the longest sequence has {rg._T} tokens but data.size(1) is {src.width}')
+
+
 def _convert(self: Z, rg: '_native.Ragged', dst: SideSpec, fill_value: Number = 0) -> Tensor:
-    spec = MapSpec(rg=rg, src=side_of(self, rg), dst=dst)
+    src = side_of(self, rg)
+    _check_source(src, rg)
+    spec = MapSpec(rg=rg, src=src, dst=dst)
     return _native.row_map(self.raw(), spec, fill_value)
 
 

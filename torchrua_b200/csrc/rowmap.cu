@@ -195,7 +195,10 @@ __device__ __forceinline__ int64_t source_row(const RowMapParams& p, int64_t i, 
   switch (p.s.layout) {
     case RUA_CAT: {
       CatOff f{rg.off, p.s.len_xform, p.s.len_arg};
-      return f(i) + ts;
+      const int64_t r = f(i) + ts;
+      // lengths that describe more tokens than the storage holds (possible only inside the speculative C -> P launch of
+      // C.pack(), before the host has seen N: the caller raises afterwards) must not read past the payload
+      return r < p.s.rows ? r : kPadRow;
     }
     case RUA_LEFT:
       return i * p.s.width + ts;
@@ -593,6 +596,7 @@ __device__ __forceinline__ void tile_body(const RowMapParams& p, OffFn f, int64_
       } else {                                   // conversions: every destination token of C / P exists in the source
         if (SRC == RUA_RIGHT && base_len < 0) base_len = __ldg(p.rg.off + i + 1) - __ldg(p.rg.off + i);
         sr = simple_source_row<SRC>(p, i, td, base_len);
+        if (SRC == RUA_CAT && sr >= p.s.rows) sr = kPadRow;   // see source_row: inconsistent lengths never read past the payload
       }
       srow[r] = sr;
     }
@@ -992,6 +996,7 @@ row_map_transpose_kernel(const RowMapParams p, const int TT_) {
         my_i = __ldg(p.rg.sorted + r);
         my_o = __ldg(off + my_i);
         my_len = __ldg(off + my_i + 1) - my_o;
+        if (!kFromPack && sq.layout == RUA_CAT && my_o + my_len > sq.rows) my_len = sq.rows > my_o ? sq.rows - my_o : 0;   // see source_row
       }
     }
     const int64_t t = t0 + tt_l;
@@ -1078,6 +1083,7 @@ row_map_transpose1_kernel(const RowMapParams p) {
       my_i = __ldg(p.rg.sorted + r);
       my_o = __ldg(off + my_i);
       my_len = __ldg(off + my_i + 1) - my_o;
+      if (!kFromPack && sq.layout == RUA_CAT && my_o + my_len > sq.rows) my_len = sq.rows > my_o ? sq.rows - my_o : 0;   // see source_row
     }
   }
   // no token of this CTA exists when the batch size at its first time step does not reach its first rank

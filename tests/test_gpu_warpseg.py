@@ -144,3 +144,29 @@ def test_ptr_and_idx_many_short_segments(rua, case):
         assert torch.equal(left.idx().data.cpu(), which * t + within)
         right = rua.R(data=pad, token_sizes=lens.cuda())
         assert torch.equal(right.idx().data.cpu(), which * t + (t - lens[which]) + within)
+
+
+# ---------------------------------------------------------------------------------------------------
+# one-vector rows into C with many short sequences (csrc/rowmap.cu: row_map_warpseg_cat1_kernel): L -> C, R -> C, C.rev, C.roll
+# ---------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize('case', sorted(SIZES))
+@pytest.mark.parametrize('dtype,feat', [(torch.long, ()), (torch.int32, ()), (torch.float32, (4,)), (torch.int16, ())])
+def test_narrow_rows_into_cat_many_short_sequences(rua, case, dtype, feat):
+    sizes = SIZES[case](np.random.default_rng(13)).astype(np.int64)
+    lens = torch.from_numpy(sizes).cuda()
+    n, b = int(sizes.sum()), sizes.size
+    g = torch.Generator(device='cuda').manual_seed(2)
+    data = torch.randint(-30000, 30000, (n,) + feat, generator=g, device='cuda').to(dtype)
+    which = torch.repeat_interleave(torch.arange(b, device='cuda'), lens)
+    start = torch.cumsum(lens, 0) - lens
+    within = torch.arange(n, device='cuda') - start[which]
+    c = rua.C(data=data, token_sizes=lens)
+    assert torch.equal(c.rev().data, data[start[which] + (lens[which] - 1 - within)])
+    for shift in (1, -3, 70):
+        assert torch.equal(c.roll(shift).data, data[start[which] + (within - shift) % lens[which]]), f'roll({shift})'
+    left, right = c.left(7), c.right(7)
+    assert torch.equal(left.cat().data, data) and torch.equal(right.cat().data, data)
+    assert torch.equal(left.cat().token_sizes, lens)
+    # a padded source whose storage is wider than the longest sequence
+    wide = rua.L(data=torch.cat([left.data, torch.full_like(left.data[:, :3], -9)], dim=1).contiguous(), token_sizes=lens)
+    assert torch.equal(wide.cat().data, data)

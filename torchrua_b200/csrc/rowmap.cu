@@ -706,6 +706,96 @@ row_map_tile_cat1_kernel(const RowMapParams p) {
   }
 }
 
+// L / R -> C, C.rev, C.roll with ONE-VECTOR rows and MANY SHORT sequences (BASELINE config 5: 1 M sequences of 1..64 token
+// ids): the decomposition of emit_ptr_warpseg_kernel (emit.cu) with the payload attached.  A warp owns 32 consecutive
+// sequences = one contiguous range of C rows; lane i reads off[s0 + i], off[s0 + i + 1] (coalesced: no search, no per-tile
+// decode chain, no block barrier), paints its lane number over its sequence's rows in a 2 KB byte window of shared memory,
+// and the warp then walks the window four rows per lane: one LDS.32 gives the four owners, a shuffle fetches each owner's
+// source constant, four loads, ONE wide store.
+constexpr int kWcThreads = 256;
+constexpr int kWcWarps = kWcThreads / 32;
+constexpr int kWcWin = 2048;   // C rows per window
+
+template <typename V, int SRC>
+__global__ void __launch_bounds__(kWcThreads)
+row_map_warpseg_cat1_kernel(const RowMapParams p) {
+  __shared__ __align__(16) unsigned char s_own[kWcWarps][kWcWin];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int64_t S = p.rg.B, n = p.d.rows;
+  const int64_t s0 = ((int64_t)blockIdx.x * kWcWarps + warp) * 32;
+  if (s0 >= S) return;                                   // warp-uniform; no block-level synchronisation below
+  const int64_t s = s0 + lane;
+  int64_t beg = s < S ? __ldg(p.rg.off + s) : n, end = s < S ? __ldg(p.rg.off + s + 1) : n;
+  const int64_t len = end - beg;
+  beg = beg < n ? beg : n;
+  end = end < n ? end : n;
+  const int64_t wbeg = shfl_i64(beg, 0), wend = shfl_i64(end, 31);
+  const int64_t W = p.s.width;
+  // source row of C row q (owned by this lane's sequence):   L: q + c   R: q + c   rev: c - q   roll: beg + (q - beg - sh) mod len
+  int64_t c = 0;
+  if (SRC == RUA_LEFT) c = s * W - beg;
+  else if (SRC == RUA_RIGHT) c = s * W + (W - len) - beg;
+  else if (SRC == kSrcCatRev) c = 2 * beg + len - 1;
+  int64_t sh = 0;
+  if (SRC == kSrcCatRoll && len > 0) { sh = p.tmap_arg % len; if (sh < 0) sh += len; }
+  const V* __restrict__ src = reinterpret_cast<const V*>(p.src);
+  V* __restrict__ dst = reinterpret_cast<V*>(p.dst);
+  unsigned char* own = s_own[warp];
+  for (int64_t w0 = wbeg & ~(int64_t)3; w0 < wend; w0 += kWcWin) {
+    const int64_t w1 = w0 + kWcWin < wend ? w0 + kWcWin : wend;
+    const unsigned who = __ballot_sync(kFullMask, beg <= w0 && end >= w0 + kWcWin);
+    if (!who) {
+      const int64_t lo64 = beg < w0 ? w0 : (beg > w1 ? w1 : beg), hi64 = end < w0 ? w0 : (end > w1 ? w1 : end);
+      int q = (int)(lo64 - w0);
+      const int hi = (int)(hi64 - w0);
+      for (; q < hi && (q & 3); ++q) own[q] = (unsigned char)lane;
+      const unsigned word = (unsigned)lane * 0x01010101u;
+      for (; q + 4 <= hi; q += 4) *reinterpret_cast<unsigned*>(own + q) = word;
+      for (; q < hi; ++q) own[q] = (unsigned char)lane;
+    }
+    __syncwarp();
+    const int groups = (int)((w1 - w0 + 3) >> 2);
+    for (int g0 = 0; g0 < groups; g0 += 32) {
+      const int g = g0 + lane;
+      int o[4];
+      if (who) {
+        o[0] = o[1] = o[2] = o[3] = __ffs(who) - 1;
+      } else {
+        const uchar4 b = reinterpret_cast<const uchar4*>(own)[g < groups ? g : 0];
+        o[0] = b.x & 31; o[1] = b.y & 31; o[2] = b.z & 31; o[3] = b.w & 31;   // unpainted bytes: any lane, never loaded
+      }
+      const int64_t q0 = w0 + 4 * (int64_t)g;
+      int64_t from[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int64_t q = q0 + e;
+        if (SRC == kSrcCatRoll) {
+          const int64_t ob = shfl_i64(beg, o[e]), ol = shfl_i64(len, o[e]), os = shfl_i64(sh, o[e]);
+          int64_t u = q - ob - os;
+          if (u < 0) u += ol;
+          from[e] = ob + u;
+        } else {
+          const int64_t oc = shfl_i64(c, o[e]);
+          from[e] = SRC == kSrcCatRev ? oc - q : q + oc;
+        }
+      }
+      if (g >= groups) continue;
+      V v[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e)
+        if (q0 + e >= wbeg && q0 + e < w1) v[e] = ld_stream(src + from[e]);
+      if (q0 >= wbeg && q0 + 4 <= w1) {
+        store4<V>(dst + q0, v[0], v[1], v[2], v[3]);
+      } else {
+#pragma unroll
+        for (int e = 0; e < 4; ++e)
+          if (q0 + e >= wbeg && q0 + e < w1) st_stream(dst + q0 + e, v[e]);
+      }
+    }
+    __syncwarp();
+  }
+}
+
 // destination C or P: segment search through shared memory
 template <typename V, int SRC>
 __global__ void __launch_bounds__(kTileThreads)
@@ -1206,6 +1296,19 @@ static void launch_narrow(RowMapParams& p, int64_t rows, cudaStream_t st) {
   const int srck = simple ? p.s.layout : (cat_select ? (p.tmap == RUA_MAP_REV ? kSrcCatRev : kSrcCatRoll) : kGenericSrc);
   const unsigned nb = (unsigned)blocks;
   if (searched) {
+    // ... with many short sequences: a warp per 32 sequences (no per-tile decode chain)
+    static const int64_t ws_min = [] { const char* e = getenv("RUA_WARPSEG_MIN_S"); return e ? atoll(e) : 32768ll; }();
+    if (p.d.layout == RUA_CAT && p.row_vecs == 1 && ((uintptr_t)p.dst & (4 * sizeof(V) - 1)) == 0 && p.rg.B >= ws_min &&
+        rows <= 256 * p.rg.B && (srck == RUA_LEFT || srck == RUA_RIGHT || srck == kSrcCatRev || srck == kSrcCatRoll)) {
+      const unsigned wb = (unsigned)ceil_div(p.rg.B, (int64_t)kWcWarps * 32);
+      switch (srck) {
+        case RUA_LEFT: row_map_warpseg_cat1_kernel<V, RUA_LEFT><<<wb, kWcThreads, 0, st>>>(p); break;
+        case RUA_RIGHT: row_map_warpseg_cat1_kernel<V, RUA_RIGHT><<<wb, kWcThreads, 0, st>>>(p); break;
+        case kSrcCatRev: row_map_warpseg_cat1_kernel<V, kSrcCatRev><<<wb, kWcThreads, 0, st>>>(p); break;
+        default: row_map_warpseg_cat1_kernel<V, kSrcCatRoll><<<wb, kWcThreads, 0, st>>>(p); break;
+      }
+      return;
+    }
     // one-vector rows into C from L / R, and C.rev / C.roll: four consecutive rows per thread, one wide store
     if (p.d.layout == RUA_CAT && ((uintptr_t)p.dst & (4 * sizeof(V) - 1)) == 0 &&
         (srck == RUA_LEFT || srck == RUA_RIGHT || (p.row_vecs == 1 && (srck == kSrcCatRev || srck == kSrcCatRoll)))) {

@@ -65,7 +65,10 @@ LIVE_CASES = [
     ('live_setitem_H512', 'setitem', dict(seed=49, B=120, lo=1, hi=0, feat=(512,), dtype='bf16'), 'exact', None),
     ('live_setitem_wide_storage_f32', 'setitem', dict(seed=50, B=300, lo=1, hi=0, feat=(3,), dtype='f32', extra_width=4), 'exact', None),
     ('live_reduce_f32_H256', 'reductions', dict(seed=51, S=700, lo=0, hi=200, feat=(256,), dtype='f32', grad=True), 'reduce', None),
-    ('live_reduce_flat', 'reductions', dict(seed=52, S=20000, lo=1, hi=64, feat=(), dtype='f32', grad=True), 'reduce', None),
+    # >= 32768 segments of per-token scalars: the warp-per-32-segments kernels, forward and backward (with empty segments)
+    ('live_reduce_flat', 'reductions', dict(seed=52, S=40000, lo=0, hi=64, feat=(), dtype='f32', grad=True), 'reduce', None),
+    ('live_reduce_flat_long_tail', 'reductions', dict(seed=59, S=33000, lo=1, hi=9, feat=(), dtype='f32', grad=True, scale=0.5), 'reduce', None),
+    ('live_reduce_flat_f64', 'reductions', dict(seed=60, S=34000, lo=0, hi=20, feat=(), dtype='f64', grad=True), 'reduce', None),
     ('live_reduce_bf16_H1024', 'reductions', dict(seed=53, S=300, lo=1, hi=512, feat=(1024,), dtype='bf16',
                                                   ops=('sum', 'mean', 'max', 'min', 'logsumexp')), 'bf16', dict(upcast=True)),
     ('live_seg', 'seg', dict(seed=54, B=40, lo=2, hi=0, feat=(16,), dtype='f32'), 'close', None),

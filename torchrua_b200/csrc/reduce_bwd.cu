@@ -252,7 +252,7 @@ int rua_segment_reduce_backward(const void* grad_out, const void* out, const voi
   uintptr_t a = (uintptr_t)grad_out | (uintptr_t)out | (uintptr_t)data | (uintptr_t)grad_data;
   bool vec = (H % full == 0) && (a & 15u) == 0;
   cudaStream_t st = (cudaStream_t)stream;
-  if (flat_supported(dtype, H) && warpseg_applies(N, S) && (((uintptr_t)data | (uintptr_t)grad_data) & 15u) == 0) {
+  if (H == 1 && warpseg_applies(N, S) && (((uintptr_t)data | (uintptr_t)grad_data) & 15u) == 0) {
     // rows no segment owns (sum of sizes < N) get no gradient; the kernel only writes rows it owns
     int rc = check_cuda(cudaMemsetAsync(grad_data, 0, 0, st));
     if (rc) return rc;

@@ -565,11 +565,12 @@ class _RowMap(torch.autograd.Function):
     def backward(ctx, grad_out: Tensor):
         spec: MapSpec = ctx.spec
         g = grad_out.contiguous()
-        if spec.pad_mode == PAD_WRAP and ctx.src_rows > 0 and g.shape[0] > 0 and g.dtype in _DTYPES:
-            # last() / segment_last of an EMPTY sequence read a wrapped row in the forward pass (select/last.py:11-13),
-            # so one source row can feed several outputs and the inverse map is not a map.  Push the source row
-            # numbers through the forward map instead and sum the gradient rows per source row (stable device sort +
-            # one gathered segment-sum launch: deterministic, no atomics); fill = one-past-the-end = dropped bucket.
+        if spec.pad_mode in (PAD_WRAP, PAD_ROW0) and ctx.src_rows > 0 and g.shape[0] > 0 and g.dtype in _DTYPES:
+            # The forward pass was not injective: last() / segment_last of an EMPTY sequence read a wrapped row
+            # (select/last.py:11-13), L / R.roll fill their padding slots with flat row 0 (select/roll.py:19-34) -- one
+            # source row feeds several outputs and the inverse map is not a map.  Push the source row numbers through the
+            # SAME forward map and sum the gradient rows per source row (stable device sort + one gathered segment-sum
+            # launch: deterministic, no atomics); fill = one-past-the-end = a bucket that is dropped.
             rows = ctx.src_rows
             ids = torch.arange(rows, dtype=torch.long, device=g.device)
             where = _row_map_raw(ids, spec, int(rows).to_bytes(8, 'little'), (), torch.long, g.device)
@@ -578,13 +579,6 @@ class _RowMap(torch.autograd.Function):
         inv = spec.inverse()
         zero = bytes(g.element_size())
         grad_src = _row_map_raw(g, inv, zero, tuple(g.shape[1:]), g.dtype, g.device)
-        if spec.pad_mode == PAD_ROW0 and grad_src.shape[0] > 0:
-            # forward copied flat row 0 into every padding slot (L/R.roll quirk): those slots' gradients
-            # flow back into row 0.  Padding slots are exactly the rows the inverse map does not reach.
-            probe = MapSpec(spec.rg, spec.src, spec.dst, spec.tmap, spec.tmap_arg, PAD_FILL)
-            ones = torch.ones((ctx.src_rows, 1), dtype=torch.uint8, device=g.device)
-            hit = _row_map_raw(ones, probe, bytes(1), (1,), torch.uint8, g.device).view(-1).bool()
-            grad_src[0] += g[~hit].sum(dim=0)
         return grad_src, None, None
 
 

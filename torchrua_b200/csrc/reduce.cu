@@ -117,6 +117,9 @@ segreduce_kernel(const T* __restrict__ data, const int64_t* __restrict__ ridx, c
           if (active) lse_batch<T, V, kRedUnroll>(raw, st.a, st.s, ext, ext2);
           done = true;
         }
+        // (round 2: batches of 4 rows / 64 registers / 8 CTAs per SM instead of 8 rows / 80 registers / 6 CTAs measured
+        // 79.2 % of peak at cfg3 against 85.2 %: the kernel is bound by issue slots and the MUFU pipe -- one EX2 per
+        // element is 1.46 ms of SFU time at 16 per clock per SM inside a 2.4 ms kernel -- not by exposed latency.)
         // (round 2: a masked batched form for boundary batches -- rows [k, e) only -- measured 81.3 % of peak at cfg3
         // against 84.6 % for the per-element update below: the kernel sits at its 80-register cap and the extra code
         // costs more than the ~13 % of rows it would speed up.  Dropped.)

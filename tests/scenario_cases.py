@@ -77,3 +77,33 @@ LIVE_CASES = [
     ('live_compose', 'compose', dict(seed=57, B=30, lo=1, hi=0, feat=(8,), dtype='f32'), 'exact', None),
     ('live_scatter', 'scatter', dict(seed=58, M=200, K=5000, feat=(16,), dtype='f32'), 'reduce', None),
 ]
+
+
+# a seeded sweep over shapes / dtypes / row widths (vector widths 1 B .. 32 B, narrow and wide kernels) against the live reference
+def _sweep():
+    import random
+    rnd = random.Random(2024)
+    feats = [(), (1,), (3,), (4,), (6,), (16,), (31,), (32,), (33,), (64,), (96,), (130,), (256,), (2, 24)]
+    dtypes = ['f32', 'bf16', 'f16', 'i64', 'i32', 'f64']
+    out = []
+    for k in range(18):
+        feat, dt = rnd.choice(feats), rnd.choice(dtypes)
+        b = rnd.choice([1, 2, 5, 17, 33, 64, 150, 700])
+        distinct = b <= 150 and rnd.random() < 0.6
+        hi = rnd.choice([3, 9, 40, 130])
+        base = dict(seed=1000 + k, B=b, lo=1, hi=0 if distinct else hi, feat=feat, dtype=dt)
+        fn = ['conversions', 'selects', 'getitem', 'setitem', 'metadata'][k % 5]
+        kw = dict(base)
+        if fn in ('conversions', 'selects', 'metadata'):
+            kw['distinct'] = distinct
+            if fn == 'selects':
+                kw['lo'] = 2
+        else:
+            kw['hi'] = 0                    # getitem / setitem scenarios draw distinct lengths themselves
+            kw['B'] = min(b, 150)
+            kw['extra_width'] = rnd.choice([0, 0, 2])
+        out.append((f'sweep{k:02d}_{fn}_{dt}_{"x".join(map(str, feat)) or "scalar"}_B{kw["B"]}', fn, kw, 'exact', None))
+    return out
+
+
+LIVE_CASES += _sweep()

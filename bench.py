@@ -595,7 +595,8 @@ def run_ours(args):
         configs['cfg4'] = cfg4_bench.run(rank, world, dev, micro_batches=args.cfg4_micro_batches)
         if world == 1:
             from benchmarks import ops as ops_bench
-            for key, fn in (('cfg3', ops_bench.cfg3), ('cfg5', ops_bench.cfg5)):
+            for key, fn in (('cfg2', lambda r, **kw: ops_bench.cfg2(r, light=True, **kw)), ('cfg3', ops_bench.cfg3),
+                            ('cfg5', ops_bench.cfg5)):
                 rows = []
                 fn(rows, reps=5, quiet=True)
                 configs[key] = ops_bench.compact(rows)

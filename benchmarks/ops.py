@@ -93,7 +93,9 @@ def row(results, cfg, name, nbytes, tokens, fn, reps, aten=None):
           flush=True)
 
 
-def cfg2(results, reps, quiet=False):
+def cfg2(results, reps, quiet=False, light=False):
+    """light: conversions, selects, masks and reductions only (the record bench.py embeds); the full table adds the list
+    constructors, strict mode, scatter_* and the backward passes."""
     global QUIET
     QUIET = quiet
     g = torch.Generator().manual_seed(0)
@@ -129,6 +131,8 @@ def cfg2(results, reps, quiet=False):
             lc = lens.cuda()
             aten = lambda fn=fn, lc=lc: torch.segment_reduce(data, fn, lengths=lc, unsafe=True)
         row(results, 2, f'segment_{fn}', nd + b * d + 8 * b, n, lambda f=f: f(data, c.token_sizes), reps, aten)
+    if light:
+        return
     # constructors from a list of 4096 tensors: host-side metadata + one multi-source kernel
     from torch.nn.utils.rnn import pack_sequence, pad_sequence
     pieces = list(torch.split(data, lens.tolist()))

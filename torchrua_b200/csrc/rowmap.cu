@@ -1142,8 +1142,10 @@ row_map_transpose_kernel(const RowMapParams p, const int TT_) {
 // one coalesced load (no change), and PERSISTENT software-pipelined CTAs that keep the next tile's loads in flight while
 // the current one is stored (40 % / 34 %: worse).  ncu shows why: the kernel moves 586 MB of DRAM traffic for 528 MB
 // of payload (64-byte DRAM granules around 256-byte runs that start at arbitrary offsets) at 3.4 TB/s -- the runs
-// belong to sequences in SORTED order, i.e. scattered over the whole C buffer, and that access pattern, not latency
-// hiding, is the ceiling.
+// belong to sequences in SORTED order, i.e. scattered over the whole C buffer.  benchmarks/transpose_locality.py then split
+// the loss: the scattering costs 6 % (C -> P) / 19 % (P -> C), RAGGEDNESS the rest -- 68 % of the (rank, step) slots of the
+// touched tiles hold a token at U[1,64], and constant lengths run at 4.75 TB/s; a compacted variant (lanes over the flattened
+// populated slots) gained 10 % / 2 % on ragged batches and lost 22-31 % on uniform ones.  Dropped as well.
 template <typename V, bool kFromPack, int KT>
 __global__ void __launch_bounds__(256, KT == 1 ? 8 : (KT == 2 ? 5 : 4))
 row_map_transpose1_kernel(const RowMapParams p) {

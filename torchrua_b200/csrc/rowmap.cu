@@ -1246,114 +1246,6 @@ row_map_transpose1_kernel(const RowMapParams p) {
   }
 }
 
-// COMPACTED variant of the above for ragged (not padded) sequence-major sides.  The ranks of a tile are neighbours in
-// sorted order, so their lengths are (nearly) equal: the populated part of a 32-rank x 64-step tile is a dense
-// rectangle 32 x m with m = len - t0 <= 64, and a length distribution such as U[1,64] leaves a third of the (rank, step)
-// slots of the touched tiles empty.  benchmarks/transpose_locality.py shows that this -- not the scattered access pattern --
-// is what the kernel pays for: 4.75 TB/s on constant lengths, 3.0-3.1 TB/s on U[1,64] whether the ranks are scattered over
-// the buffer or perfectly local (68 % of the slots are tokens: 4.75 x 0.68 = 3.2).  So the sequence-major phase maps lanes to
-// the FLATTENED (rank, step < m) slots of the warp's four ranks instead of one step per lane: every load / store instruction
-// is full, and their number is proportional to the tokens, not to the slots.
-template <typename V, bool kFromPack>
-__global__ void __launch_bounds__(256, 5)
-row_map_transpose1c_kernel(const RowMapParams p) {
-  constexpr int kSteps = 64;                          // time steps per CTA
-  __shared__ V tile[kSteps][33];                      // [time step][rank] (+1: bank skew)
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int64_t r0 = (int64_t)blockIdx.x * 32, t0 = (int64_t)blockIdx.y * kSteps;
-  const rua_side_t& sq = kFromPack ? p.d : p.s;      // the sequence-major side (C, or an L / R SOURCE)
-  const int64_t B = p.rg.B, Tp = p.rg.Tp, W = sq.width;
-  const int64_t* __restrict__ poff = p.rg.poff;
-  const int64_t* __restrict__ off = p.rg.off;
-  const V* __restrict__ src = reinterpret_cast<const V*>(p.src);
-  V* __restrict__ dst = reinterpret_cast<V*>(p.dst);
-
-  // both metadata chains start now.  pack side: this warp's time steps are tt = warp + 8 q (q < 8); lane q fetches poff
-  int64_t my_pt = 0, my_bst = 0;
-  if (lane < 8) {
-    const int64_t t = t0 + warp + 8 * lane;
-    if (t < Tp) { my_pt = __ldg(poff + t); my_bst = __ldg(poff + t + 1) - my_pt; }
-  }
-  // sequence side: this warp's ranks are r0 + warp + 8 k (k < 4); lane k fetches sorted -> off
-  int64_t my_i = 0, my_o = 0, my_len = 0;
-  if (lane < 4) {
-    const int64_t r = r0 + warp + 8 * lane;
-    if (r < B) {
-      my_i = __ldg(p.rg.sorted + r);
-      my_o = __ldg(off + my_i);
-      my_len = __ldg(off + my_i + 1) - my_o;
-      if (!kFromPack && sq.layout == RUA_CAT && my_o + my_len > sq.rows) my_len = sq.rows > my_o ? sq.rows - my_o : 0;   // see source_row
-    }
-  }
-  {
-    const int64_t bs0 = t0 < Tp ? __ldg(poff + t0 + 1) - __ldg(poff + t0) : 0;
-    if (bs0 <= r0) return;                           // CTA-uniform: no token of this tile exists
-  }
-  // m = populated steps of this warp's ranks inside the tile (the longest of the four: rank warp, they are sorted)
-  int m;
-  {
-    int64_t l0 = shfl_i64(my_len, 0) - t0;
-    m = l0 <= 0 ? 0 : (l0 > kSteps ? kSteps : (int)l0);
-  }
-  const unsigned recip = m > 0 ? 65536u / (unsigned)m + 1u : 0u;    // j / m == (j * recip) >> 16 for j < 256, m <= 64
-  const int slots = 4 * m;                                          // flattened (k, step) slots of this warp
-  auto slot = [&](int j, int& k, int& tt) { k = (int)(((unsigned)j * recip) >> 16); tt = j - k * m; };
-  auto seq_row = [&](int64_t i, int64_t o, int64_t len, int64_t t) -> int64_t {
-    return sq.layout == RUA_CAT ? o + t : (sq.layout == RUA_LEFT ? i * W + t : i * W + (W - len) + t);
-  };
-
-  if (kFromPack) {   // ---- P -> C: read P along ranks (empty time steps are skipped warp-uniformly), write C compacted ----
-    V val[8];
-    unsigned on = 0;
-#pragma unroll
-    for (int q = 0; q < 8; ++q) {
-      const int64_t pt = shfl_i64(my_pt, q), bst = shfl_i64(my_bst, q);
-      if (bst <= r0) break;                          // warp-uniform: batch sizes do not increase with time
-      if (r0 + lane < bst) { on |= 1u << q; val[q] = ld_stream(src + pt + r0 + lane); }
-    }
-#pragma unroll
-    for (int q = 0; q < 8; ++q)
-      if (on >> q & 1u) tile[warp + 8 * q][lane] = val[q];
-    __syncthreads();
-    for (int j0 = 0; j0 < slots; j0 += 32) {         // warp-uniform trip count: the shuffles below need every lane
-      const int j = j0 + lane;
-      int k = 0, tt = 0;
-      if (j < slots) slot(j, k, tt);
-      const int64_t i = shfl_i64(my_i, k), o = shfl_i64(my_o, k), len = shfl_i64(my_len, k);
-      const int64_t t = t0 + tt;
-      if (j < slots && r0 + warp + 8 * k < B && t < len) st_stream(dst + seq_row(i, o, len, t), tile[tt][warp + 8 * k]);
-    }
-  } else {           // ---- C / L / R -> P: read the sequence-major side compacted, write P along ranks ----------------
-    V val[8];
-    unsigned on = 0;
-#pragma unroll
-    for (int q = 0; q < 8; ++q) {
-      const int j = lane + 32 * q;
-      if (32 * q >= slots) break;                    // warp-uniform
-      int k = 0, tt = 0;
-      if (j < slots) slot(j, k, tt);
-      const int64_t i = shfl_i64(my_i, k), o = shfl_i64(my_o, k), len = shfl_i64(my_len, k);
-      const int64_t t = t0 + tt;
-      if (j < slots && r0 + warp + 8 * k < B && t < len) { on |= 1u << q; val[q] = ld_stream(src + seq_row(i, o, len, t)); }
-    }
-#pragma unroll
-    for (int q = 0; q < 8; ++q) {
-      if (on >> q & 1u) {
-        int k, tt;
-        slot(lane + 32 * q, k, tt);
-        tile[tt][warp + 8 * k] = val[q];
-      }
-    }
-    __syncthreads();
-#pragma unroll
-    for (int q = 0; q < 8; ++q) {
-      const int64_t pt = shfl_i64(my_pt, q), bst = shfl_i64(my_bst, q);
-      if (bst <= r0) break;                          // warp-uniform
-      if (r0 + lane < bst) st_stream(dst + pt + r0 + lane, tile[warp + 8 * q][lane]);
-    }
-  }
-}
-
 // can the ragged transpose serve this call?  (identity token map, untransformed lengths, narrow rows)
 static bool transpose_applies(const RowMapParams& p, int64_t* grid_y, int* tt) {
   if (p.gather_index || p.scatter_index || p.row_vecs < 1 || p.row_vecs > 7) return false;
@@ -1379,12 +1271,7 @@ static void launch_narrow(RowMapParams& p, int64_t rows, cudaStream_t st) {
     p.div_rv_m = dv.m; p.div_rv_s = dv.s;
     dim3 grid((unsigned)ceil_div(p.rg.B, 32), (unsigned)gy);
     const bool from_pack = p.s.layout == RUA_PACK;
-    if (p.row_vecs == 1 && !(from_pack && p.d.layout != RUA_CAT)) {
-      // one-vector rows, ragged sequence-major side: lanes walk the FLATTENED populated slots of a 32-rank x 64-step tile
-      dim3 gc((unsigned)ceil_div(p.rg.B, 32), (unsigned)ceil_div(gy * tt, 64));
-      if (from_pack) row_map_transpose1c_kernel<V, true><<<gc, 256, 0, st>>>(p);
-      else row_map_transpose1c_kernel<V, false><<<gc, 256, 0, st>>>(p);
-    } else if (p.row_vecs == 1) {
+    if (p.row_vecs == 1) {
       // one-vector rows: KT time tiles of 32 steps per CTA, all of their row loads in flight together
       constexpr int kMaxKT = sizeof(V) >= 16 ? 2 : 4;   // 48 KB of static shared memory
       const int kt = gy <= 1 ? 1 : ((gy <= 2 || kMaxKT == 2) ? 2 : 4);

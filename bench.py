@@ -684,16 +684,8 @@ def time_output_gather(args, step, data, lens, lens_host, glens, parts, rank, wo
     # micro-batches of the local shard: consecutive runs of sequences with ~equal token counts.  The fused R -> C +
     # peer-store kernel of micro-batch k runs on a side stream (NVLink-bound) while the conversions of micro-batch k+1
     # and the reductions of micro-batch k-1 run on the main stream (HBM-bound): the wire never waits for compute.
-    kmb = max(1, min(args.gather_micro_batches, lens_host.numel()))
-    csum = torch.cumsum(lens_host, 0)
-    n_local = int(csum[-1])
-    cuts, start = [], 0
-    for k in range(kmb):
-        end = lens_host.numel() if k == kmb - 1 else int(torch.searchsorted(csum, n_local * (k + 1) // kmb, right=True))
-        end = max(end, start + 1) if start < lens_host.numel() else start
-        if end > start:
-            cuts.append((start, end, int(csum[start - 1]) if start else 0, int(csum[end - 1])))
-        start = end
+    cuts = shard.micro_batch_cuts(lens_host, args.gather_micro_batches)
+    n_local = int(lens_host.sum())
     ids_local = parts[rank].to(dev)
     side = torch.cuda.Stream(dev, priority=-1)        # the wire-bound gather gets CTA slots as soon as they free up
 

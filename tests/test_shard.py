@@ -92,3 +92,23 @@ def test_exchanges_gloo_world2():
         results = m.dict()
         mp.spawn(_worker, args=(world, port, results), nprocs=world, join=True)
         assert all(results.get(r) for r in range(world))
+
+
+def test_micro_batch_cuts_cover_every_sequence_once():
+    """host-side plumbing of the overlapped output gather (bench.py: fused_step)"""
+    import torch
+    from torchrua_b200 import shard
+    g = torch.Generator().manual_seed(0)
+    for b, k in ((1, 4), (3, 8), (10, 1), (4096, 4), (4096, 7), (5, 5), (100, 3)):
+        lens = torch.randint(0 if b > 3 else 1, 50, (b,), generator=g)
+        cuts = shard.micro_batch_cuts(lens, k)
+        assert 1 <= len(cuts) <= min(k, b)
+        assert cuts[0][0] == 0 and cuts[-1][1] == b and cuts[0][2] == 0 and cuts[-1][3] == int(lens.sum())
+        for (a0, a1, t0, t1), nxt in zip(cuts, cuts[1:] + [None]):
+            assert a1 > a0 and t1 - t0 == int(lens[a0:a1].sum())
+            if nxt is not None:
+                assert nxt[0] == a1 and nxt[2] == t1
+        if b >= 1000:          # balanced to within one sequence
+            sizes = [t1 - t0 for _, _, t0, t1 in cuts]
+            assert max(sizes) - min(sizes) <= 2 * int(lens.max())
+    assert shard.micro_batch_cuts(torch.zeros(0, dtype=torch.long), 4) == []

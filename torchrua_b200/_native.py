@@ -433,7 +433,6 @@ def ragged_from_pack(batch_sizes: Tensor, sorted_indices: Optional[Tensor], unso
     hit = _cache_get(key, 'pack')
     if hit is not None and hit.bs_cpu is batch_sizes:
         return hit
-    lib = _lib.load()
     bs_cpu = batch_sizes.detach()
     if bs_cpu.is_cuda:
         bs_cpu = bs_cpu.cpu()

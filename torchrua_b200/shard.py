@@ -39,6 +39,32 @@ def partition_imbalance(lengths: Tensor, parts: List[Tensor]) -> float:
     return float(tokens.max() / tokens.mean()) if tokens.numel() and float(tokens.mean()) > 0 else 1.0
 
 
+def micro_batch_cuts(lengths: Tensor, k: int) -> List[Tuple[int, int, int, int]]:
+    """Cut a rank's sequences (host lengths, in local order) into at most ``k`` consecutive runs holding about the same number
+    of tokens each: ``(first sequence, one past the last, first token, one past the last token)`` per run.  Every sequence
+    lands in exactly one run; runs are never empty.  The output gather walks these micro-batches: the peer stores of one
+    overlap the conversions of the next."""
+    lengths = lengths.detach().cpu().long()
+    b = lengths.numel()
+    if b == 0:
+        return []
+    k = max(1, min(int(k), b))
+    csum = torch.cumsum(lengths, 0)
+    total = int(csum[-1])
+    cuts, start = [], 0
+    for j in range(k):
+        if start >= b:
+            break
+        end = b if j == k - 1 else int(torch.searchsorted(csum, total * (j + 1) // k, right=True))
+        end = min(max(end, start + 1), b)
+        cuts.append((start, end, int(csum[start - 1]) if start else 0, int(csum[end - 1])))
+        start = end
+    if cuts and cuts[-1][1] < b:      # rounding left a tail: it joins the last run
+        s0, _, t0, _ = cuts[-1]
+        cuts[-1] = (s0, b, t0, total)
+    return cuts
+
+
 def take_sequences(data: Tensor, token_sizes: Tensor, ids: Tensor) -> Tuple[Tensor, Tensor]:
     """host-side helper: the (data, token_sizes) of a CattedSequence restricted to sequences ``ids``."""
     off = torch.cumsum(token_sizes, 0) - token_sizes

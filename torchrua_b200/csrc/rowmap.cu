@@ -513,66 +513,6 @@ row_map_multi_kernel(const RowMapParams p, const MultiDst m) {
   }   // grid-stride loop over the warps' row groups
 }
 
-// The same gather with the rows moved by the TMA engine instead of by SM load / store instructions: one lane per warp
-// issues, per row, ONE bulk copy global -> shared (completion on the warp's mbarrier) and then one bulk copy shared ->
-// global PER DESTINATION (peer windows over NVLink, the local window, the local copy), tracked by bulk async-groups with
-// two row buffers per warp.  The kernel is bound by the wire, so a warp only has to keep a few KB in flight; what the bulk
-// stores change is the shape of the traffic: whole rows leave the SM as contiguous bursts instead of 32-byte stores.
-constexpr int kMultiTmaWarps = 4;
-__global__ void __launch_bounds__(kMultiTmaWarps * 32)
-row_map_multi_tma_kernel(const RowMapParams p, const MultiDst m, const int row_bytes) {
-  extern __shared__ __align__(128) unsigned char s_rows[];          // kMultiTmaWarps x 2 x row_bytes
-  __shared__ __align__(8) uint64_t s_bar[kMultiTmaWarps];
-  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-  const int64_t rows = p.d.rows;
-  const int64_t warps_total = (int64_t)gridDim.x * kMultiTmaWarps;
-  unsigned char* buf = s_rows + (size_t)wib * 2 * row_bytes;
-  uint64_t* bar = &s_bar[wib];
-  if (lane == 0) mbar_init(bar, 1);
-  __syncwarp();
-  uint32_t phase = 0;
-  int which = 0;                                         // row buffer in use
-  const int n = m.n;
-  for (int64_t warp = (int64_t)blockIdx.x * kMultiTmaWarps + wib; warp * 32 < rows; warp += warps_total) {
-    const int64_t j0 = warp * 32;
-    // phase 1: one lane per local cat row decodes (sequence, token) and the source row
-    int64_t srow = kNoRow, seq = 0, tok = 0;
-    {
-      const int64_t j = j0 + lane;
-      if (j < rows) {
-        GlobalOff f{p.rg.off};
-        seq = owner_search(f, p.rg.B, j);
-        const int64_t o = f(seq);
-        tok = j - o;
-        srow = source_row(p, seq, tok, f(seq + 1) - o);
-      }
-    }
-    // phase 2: lane 0 moves the rows one by one through the two buffers
-    const int k0 = (int)(warp % n);                      // neighbouring warps start with different peers
-    for (int r = 0; r < 32; ++r) {
-      const int64_t s = shfl_i64(srow, r), si = shfl_i64(seq, r), st = shfl_i64(tok, r);
-      if (s < 0) continue;                               // warp-uniform
-      if (lane == 0) {
-        unsigned char* b = buf + (size_t)which * row_bytes;
-        bulk_wait_read<1>();                             // the stores that last read THIS buffer are done with it
-        mbar_expect_tx(bar, (uint32_t)row_bytes);
-        bulk_g2s(b, p.src + s * (int64_t)row_bytes, (uint32_t)row_bytes, bar);
-        mbar_wait(bar, phase);
-        const int64_t jl = j0 + r;
-        for (int kk = 0; kk < n; ++kk) {
-          const int k = k0 + kk < n ? k0 + kk : k0 + kk - n;
-          const int64_t dj = m.base[k] ? __ldg(m.base[k] + si) + st : jl;
-          bulk_s2g(m.dst[k] + dj * (int64_t)row_bytes, b, (uint32_t)row_bytes);
-        }
-        bulk_commit();
-      }
-      phase ^= 1u;
-      which ^= 1;
-    }
-  }
-  if (lane == 0) bulk_wait<0>();                         // every row has landed before the warp retires
-}
-
 // ------------------------------------------------------------------------------------------------
 // narrow rows (< 128 bytes: token ids, indices, scalars -- BASELINE config 5).  A 20-step binary
 // search per 8-byte row would dominate, so here a CTA owns a TILE of consecutive destination
@@ -1520,16 +1460,8 @@ static int launch_row_map_multi(RowMapParams& p, const MultiDst& m, int64_t row_
   if (rows <= 0 || row_bytes <= 0) return RUA_OK;
   uintptr_t a = (uintptr_t)p.src | (uintptr_t)row_bytes;
   for (int k = 0; k < m.n; ++k) a |= (uintptr_t)m.dst[k];
-  // RUA_MULTI_TMA=1: rows of 16-byte multiples up to 5 KB travel as TMA bulk copies (one per destination)
-  static const int use_tma = [] { const char* e = getenv("RUA_MULTI_TMA"); return e ? atoi(e) : 0; }();
-  if (use_tma && !m.rows_are_sequences && (a & 15u) == 0 && row_bytes <= 5120) {
-    static const int tma_ctas_per_sm = [] { const char* e = getenv("RUA_MULTI_CTAS_PER_SM"); return e && atoi(e) > 0 ? atoi(e) : 4; }();
-    int64_t blocks = ceil_div(ceil_div(rows, 32), kMultiTmaWarps);
-    if (blocks > (int64_t)kNumSMs * tma_ctas_per_sm) blocks = (int64_t)kNumSMs * tma_ctas_per_sm;
-    const size_t smem = (size_t)kMultiTmaWarps * 2 * (size_t)row_bytes;
-    row_map_multi_tma_kernel<<<(unsigned)blocks, kMultiTmaWarps * 32, smem, st>>>(p, m, (int)row_bytes);
-    return check_launch();
-  }
+  // (a TMA bulk-copy variant of this kernel -- one cp.async.bulk per row and destination -- measured 25.6-26.3 ms vs 25.3 ms
+  //  at 8 GPUs: the wire, not the store shape, bounds it; profiles/r2_gather_sweep.md)
   int vec = row_bytes >= 128 ? 32 : 16;
   while (vec > 1 && (a & (uintptr_t)(vec - 1))) vec >>= 1;
   p.row_vecs = row_bytes / vec;

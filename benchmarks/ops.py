@@ -133,6 +133,17 @@ def cfg2(results, reps, quiet=False, light=False):
         row(results, 2, f'segment_{fn}', nd + b * d + 8 * b, n, lambda f=f: f(data, c.token_sizes), reps, aten)
     if light:
         return
+    # .seg(duration, segment_mean) pooling: every sequence cut into pieces of 8 tokens.  On a P the
+    # reducer gathers the packed rows itself; "unfused" is the reference's composition P -> C, reduce, C -> P.
+    cuts = [[8] * (l // 8) + ([l % 8] if l % 8 else []) for l in lens.tolist()]
+    dur = rua.C(data=torch.tensor([x for q in cuts for x in q], device='cuda'),
+                token_sizes=torch.tensor([len(q) for q in cuts], device='cuda'))
+    s_rows = int(dur.data.numel())
+    seg_bytes = nd + 3 * s_rows * d + 8 * s_rows          # data read, result written, result packed (read + write)
+    row(results, 2, 'C.seg(8-token pieces, mean)', nd + s_rows * d + 8 * s_rows, n, lambda: c.seg(dur, rua.segment_mean), reps)
+    row(results, 2, 'P.seg(8-token pieces, mean)', seg_bytes, n, lambda: srcs['P'].seg(dur, rua.segment_mean), reps)
+    row(results, 2, 'P.seg unfused (P->C, reduce, C->P)', seg_bytes, n,
+        lambda: srcs['P'].cat().seg(dur, rua.segment_mean).pack(), reps)
     # constructors from a list of 4096 tensors: host-side metadata + one multi-source kernel
     from torch.nn.utils.rnn import pack_sequence, pad_sequence
     pieces = list(torch.split(data, lens.tolist()))

@@ -112,3 +112,63 @@ def test_compose_backward_reaches_every_source(rua):
     for k, x in enumerate(leaves):
         exp = torch.cat([by_seq[j] for j in range(starts[k], starts[k] + counts[k])], dim=0)
         assert torch.equal(x.grad, exp)
+
+
+def _durations(rua, lens, piece, seed):
+    g = torch.Generator().manual_seed(seed)
+    cuts = []
+    for n in lens.tolist():
+        q, left = [], n
+        while left > 0:
+            k = min(left, int(torch.randint(1, piece + 1, (1,), generator=g)))
+            q.append(k)
+            left -= k
+        cuts.append(torch.tensor(q).cuda())
+    return rua.C.new(cuts)
+
+
+@pytest.mark.parametrize('feat,dtype', [((64,), torch.float32), ((256,), torch.bfloat16), ((), torch.float32), ((5,), torch.float64)])
+@pytest.mark.parametrize('dkind', 'CLPR')
+def test_pack_seg_gathers_instead_of_unpacking(rua, feat, dtype, dkind):
+    """P.seg(duration, segment_*) reduces straight from the packed rows (rua_segment_reduce_gather over P.idx());
+    it must give what the reference's composition P -> C, reduce, C -> P (segment.py:32-33) gives, for all six
+    reducers and any layout of the durations (max / min / last bit for bit, sums within the reduction tolerances)."""
+    g = torch.Generator().manual_seed(11)
+    lens = torch.randperm(70, generator=g)[:45] + 1
+    data = torch.randn((int(lens.sum()),) + feat, generator=g).to(dtype).cuda()
+    c = rua.C(data=data, token_sizes=lens.cuda())
+    p = c.pack()
+    dur = build(rua, dkind, _durations(rua, lens, 6, 5))
+    for fn in ('sum', 'mean', 'prod', 'max', 'min', 'logsumexp', 'last'):
+        f = getattr(rua, 'segment_' + fn)
+        got = p.seg(dur, f)
+        want = c.seg(dur, f).pack()
+        assert isinstance(got, rua.P) and torch.equal(got.batch_sizes, want.batch_sizes)
+        assert torch.equal(got.sorted_indices, want.sorted_indices) and torch.equal(got.unsorted_indices, want.unsorted_indices)
+        assert got.data.dtype == want.data.dtype and got.data.shape == want.data.shape
+        if fn in ('max', 'min', 'last'):
+            assert torch.equal(got.data, want.data), fn
+        else:       # same fp32 / fp64 accumulation, possibly another association order (DESIGN.md section 4 tolerances)
+            tol = {torch.float32: 1e-5, torch.float64: 1e-12, torch.bfloat16: 1e-2}[dtype]
+            assert torch.allclose(got.data.double(), want.data.double(), rtol=tol, atol=tol), fn
+    # a user-defined reducer keeps the generic path
+    got = p.seg(dur, lambda t, s: rua.segment_sum(t, s) * 2)
+    assert torch.equal(got.data, (c.seg(dur, rua.segment_sum).pack().data * 2))
+
+
+def test_pack_seg_gradient(rua):
+    g = torch.Generator().manual_seed(12)
+    lens = torch.randperm(40, generator=g)[:23] + 1
+    base = torch.randn((int(lens.sum()), 32), generator=g).cuda()
+    dur = _durations(rua, lens, 5, 6)
+    for fn in ('sum', 'mean', 'max', 'logsumexp'):
+        f = getattr(rua, 'segment_' + fn)
+        grads = []
+        for fused in (True, False):
+            x = base.clone().requires_grad_(True)
+            p = rua.C(data=x, token_sizes=lens.cuda()).pack()
+            out = p.seg(dur, f) if fused else p.cat().seg(dur, f).pack()
+            w = torch.randn(out.data.shape, generator=torch.Generator().manual_seed(13)).cuda()
+            (out.data * w).sum().backward()
+            grads.append(x.grad)
+        assert torch.allclose(grads[0], grads[1], rtol=1e-6, atol=1e-6), fn

@@ -5,6 +5,7 @@ streams, autograd graph); every byte of the hot path is moved or reduced by libr
 No CPU path exists: non-CUDA tensors raise ``RuntimeError``.
 """
 import ctypes
+import itertools
 import weakref
 from dataclasses import dataclass, field
 from typing import Optional, Tuple
@@ -161,17 +162,22 @@ class _Notices:
         _lib.check(lib.rua_pinned_alloc(24 * self.RING, ctypes.byref(host), ctypes.byref(dev)), 'rua_pinned_alloc')
         self.host, self.dev = host.value, dev.value
         self.slots = [(ctypes.c_int64 * 3).from_address(self.host + 24 * k) for k in range(self.RING)]
-        self.count = 0
+        self.issued = 0
+        self._tickets = itertools.count(1)      # next() on it is atomic under the GIL: two threads never share a ticket
 
     def take(self):
-        k = self.count % self.RING
-        self.count += 1
-        return self.slots[k], self.dev + 24 * k, self.count     # (host view, device address, ticket)
+        ticket = next(self._tickets)
+        self.issued = ticket
+        k = (ticket - 1) % self.RING
+        return self.slots[k], self.dev + 24 * k, ticket         # (host view, device address, ticket)
 
     @classmethod
     def read(cls, note):
         """-> (sum, max) or None (slot reused / timed out: use the device-side stats)."""
         slot, ticket = note
+        ring = _NOTICES
+        if ring is None or ring.issued - ticket >= cls.RING - 16:
+            return None                 # the slot has been (or is about to be) handed to a newer scan: its words may change under us
         for _ in range(cls.SPINS):
             seen = slot[2]
             if seen == ticket:
@@ -1224,6 +1230,17 @@ class _ScatterReduce(torch.autograd.Function):
                            'rua_segment_reduce_backward')
             scatter_rows_(grad, srt, grad_ordered)
         return grad, None, None, None, None
+
+
+def segment_reduce_gathered(source: Tensor, rows: Tensor, segment_sizes: Tensor, op: str) -> Tensor:
+    """segment_reduce(source[rows], segment_sizes, op) without materialising ``source[rows]``: the kernel reads row
+    ``rows[j]`` where the plain reduction reads row ``j``.  ``rows`` must not repeat (backward scatters the gradient rows)."""
+    require_cuda(source, rows, segment_sizes)
+    rg = ragged_from_lengths(segment_sizes)
+    rows = _i64(rows).view(-1)
+    if source.requires_grad and torch.is_grad_enabled():
+        return _ScatterReduce.apply(source, rows, rg.off, rg.B, _OPS[op])
+    return _reduce_gather_raw(source if source.is_contiguous() else source.contiguous(), rows, rg.off, rg.B, _OPS[op])
 
 
 def scatter_reduce(source: Tensor, index: Tensor, buckets: int, op: str):

@@ -1,9 +1,17 @@
 """`.seg(duration, fn)` -- mirror of torchrua/segment.py: reduce each sequence over sub-segments whose
 sizes are themselves a ragged sequence.  Thin dispatcher; the work is in the native conversions of
-``duration`` and in one native ``fn`` call."""
+``duration`` and in one native ``fn`` call.  P.seg with one of this package's own reducers skips the P -> C pass:
+the reduce kernel gathers the packed rows in sequence order itself ("seg(mean) -> pooling")."""
 import torch
 
+from torchrua_b200 import _native, reduce as _reduce
 from torchrua_b200.layout import C, L, P, R, Z
+
+# reducers whose gathered form exists natively (rua_segment_reduce_gather): fn -> op name
+_GATHERED = {
+    _reduce.segment_sum: 'sum', _reduce.segment_mean: 'mean', _reduce.segment_prod: 'prod',
+    _reduce.segment_max: 'max', _reduce.segment_min: 'min', _reduce.segment_logsumexp: 'logsumexp',
+}
 
 
 def cat_seg(self: C, duration: Z, fn) -> C:
@@ -37,6 +45,16 @@ L.seg = left_seg
 
 
 def pack_seg(self: P, duration: Z, fn) -> P:
+    # reference (segment.py:32-33): P -> C (2 N D bytes), reduce, C -> P.  The time-major rows never need to be
+    # materialised sequence-major: reduce over `P.idx()` in sequence order (N int64 instead of the N D payload pass).
+    try:
+        op = _GATHERED.get(fn)
+    except TypeError:               # an unhashable callable
+        op = None
+    if op is not None and self.data.is_cuda and self.data.dtype in _native._DTYPES and not _native.STRICT_REDUCTIONS:
+        duration = duration.cat()
+        rows = self.idx().cat().data
+        return duration._replace(data=_native.segment_reduce_gathered(self.data, rows, duration.data, op)).pack()
     return self.cat().seg(duration, fn).pack()
 
 

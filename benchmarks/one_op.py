@@ -56,6 +56,15 @@ elif name.startswith('cfg3'):
     sz = torch.from_numpy(sizes).cuda()
     op = name.split('_', 1)[1]
     fn = lambda: getattr(rua, 'segment_' + op)(x, sz)
+elif name.startswith('pool'):      # sub-word -> word pooling: cfg2 payload, segments of 1..4 rows; pool_<op>
+    gp = torch.Generator().manual_seed(5)
+    n = 1043469
+    short = torch.randint(1, 5, (n,), generator=gp)
+    short = short[:int(torch.searchsorted(short.cumsum(0), n))]
+    short = torch.cat([short, torch.tensor([n - int(short.sum())])]).cuda()
+    x = torch.randn((n, 1024), device='cuda').to(torch.bfloat16)
+    op = name.split('_', 1)[1]
+    fn = lambda: getattr(rua, 'segment_' + op)(x, short)
 else:
     raise SystemExit(f'unknown op {name}')
 

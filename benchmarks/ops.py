@@ -54,6 +54,7 @@ def timed(fn, reps, clear=True):
 
 
 QUIET = False
+ONLY = None      # --only: time just the rows whose name contains one of these substrings
 
 
 def compact(rows):
@@ -73,6 +74,8 @@ def compact(rows):
 
 
 def row(results, cfg, name, nbytes, tokens, fn, reps, aten=None):
+    if ONLY and not any(k in name for k in ONLY):
+        return
     api_ms, ker_ms = timed(fn, reps)
     r = {'cfg': cfg, 'op': name, 'api_ms': api_ms, 'kernel_ms': ker_ms, 'alg_GB': nbytes / 1e9,
          'api_GBs': nbytes / api_ms / 1e6, 'kernel_GBs': nbytes / ker_ms / 1e6 if ker_ms == ker_ms else None,
@@ -144,6 +147,22 @@ def cfg2(results, reps, quiet=False, light=False):
     row(results, 2, 'P.seg(8-token pieces, mean)', seg_bytes, n, lambda: srcs['P'].seg(dur, rua.segment_mean), reps)
     row(results, 2, 'P.seg unfused (P->C, reduce, C->P)', seg_bytes, n,
         lambda: srcs['P'].cat().seg(dur, rua.segment_mean).pack(), reps)
+    # sub-word -> word pooling: very short segments (1..4 rows of 2 KB), the common use of segment_mean / .seg
+    gp = torch.Generator().manual_seed(5)
+    short = torch.randint(1, 5, (n,), generator=gp)
+    short = short[:int(torch.searchsorted(short.cumsum(0), n))]
+    short = torch.cat([short, torch.tensor([n - int(short.sum())])]).cuda()
+    s_short = int(short.numel())
+    for fn in ('mean', 'max', 'logsumexp'):
+        f = getattr(rua, 'segment_' + fn)
+        aten = (lambda fn=fn: torch.segment_reduce(data, fn, lengths=short, unsafe=True)) if fn != 'logsumexp' else None
+        row(results, 2, f'segment_{fn} (pieces U[1,4])', nd + s_short * d + 8 * s_short, n, lambda f=f: f(data, short), reps, aten)
+    for piece in (8, 16, 32):
+        q = torch.full((n // piece,), piece)
+        q = torch.cat([q, torch.tensor([n - int(q.sum())])]).cuda() if n % piece else q.cuda()
+        for fn in ('mean', 'logsumexp'):
+            f = getattr(rua, 'segment_' + fn)
+            row(results, 2, f'segment_{fn} (pieces of {piece})', nd + int(q.numel()) * (d + 8), n, lambda f=f, q=q: f(data, q), reps)
     # constructors from a list of 4096 tensors: host-side metadata + one multi-source kernel
     from torch.nn.utils.rnn import pack_sequence, pad_sequence
     pieces = list(torch.split(data, lens.tolist()))
@@ -276,7 +295,10 @@ def main():
     ap.add_argument('--cfg', type=int, nargs='+', default=[2, 3, 5])
     ap.add_argument('--reps', type=int, default=10)
     ap.add_argument('--out', default=None)
+    ap.add_argument('--only', nargs='+', default=None, help='substrings of the row names to time')
     args = ap.parse_args()
+    global ONLY
+    ONLY = args.only
     results = []
     for k in args.cfg:
         {2: cfg2, 3: cfg3, 5: cfg5}[k](results, args.reps)

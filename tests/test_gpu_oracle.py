@@ -163,6 +163,14 @@ REDUCE_CASES = [
     ('bf16_wide', lambda r: np.minimum(r.zipf(1.5, 200), 2048), (512,), torch.bfloat16),
     ('f16', lambda r: r.integers(1, 100, 50), (40,), torch.float16),
     ('bf16_odd', lambda r: r.integers(1, 100, 50), (7,), torch.bfloat16),
+    # average segment below 16 rows: the SHORT instance of the main kernel (csrc/reduce_short.cu), many chunks, rows
+    # spanning the whole CTA and rows packed several to a CTA, empty segments, a few long segments crossing many chunks
+    ('pooling_bf16', lambda r: r.integers(1, 5, 20000), (256,), torch.bfloat16),
+    ('pooling_f32_empties', lambda r: r.integers(0, 4, 30000), (64,), torch.float32),
+    ('pooling_f16_wide', lambda r: r.integers(1, 4, 5000), (1024,), torch.float16),
+    ('pooling_f64', lambda r: r.integers(1, 6, 8000), (16,), torch.float64),
+    ('pieces8_bf16', lambda r: r.integers(7, 10, 4000), (128,), torch.bfloat16),
+    ('short_with_giants', lambda r: np.concatenate([r.integers(1, 4, 9000), [5000, 1, 0, 3000], r.integers(0, 3, 9000)]), (96,), torch.float32),
 ]
 
 

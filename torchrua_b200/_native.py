@@ -1188,9 +1188,12 @@ def _reduce_gather_raw(data: Tensor, row_index: Tensor, off: Tensor, S: int, op:
     with _on(data.device):
         nbytes = lib.rua_segment_reduce_workspace_bytes(N, S, H, dt, op)
         ws = torch.empty(nbytes, dtype=torch.uint8, device=data.device)
+        prof = _profile_begin()
         _lib.check(lib.rua_segment_reduce_gather(_ptr(data), row_index.data_ptr(), off.data_ptr(), N, S, H, dt, op,
                                                  out.data_ptr(), ws.data_ptr(), nbytes, _stream()),
                    'rua_segment_reduce_gather')
+        if prof is not None:
+            _profile_end(prof, 'segment_reduce_gather', (N + S) * H * data.element_size() + 8 * (S + N))
     return out
 
 

@@ -33,153 +33,17 @@ int flat_launch(int32_t dtype, int64_t H, int32_t op, const void* data, const in
 bool warpseg_applies(int64_t N, int64_t S);
 int warpseg_launch(int32_t dtype, int64_t H, int32_t op, const void* data, const int64_t* off, int64_t N, int64_t S,
                    void* out, void* hdr, cudaStream_t st);
+// ... and wide rows in very short segments on the SHORT instance of the main kernel (reduce_short.cu)
+bool short_applies(int64_t N, int64_t S, int32_t op);
+int short_launch(int32_t dtype, int32_t op, bool gather, bool packed, dim3 grid, int threads, const void* data,
+                 const int64_t* ridx, const int64_t* off, int64_t N, int64_t S, int64_t H, int R, void* out, void* head,
+                 void* tail, int64_t* tail_seg, void* hdr, int lanes_log2, int64_t chunks, cudaStream_t st);
 
-// ---------------------------------------------------------------------------------------------
-// main kernel
-// ---------------------------------------------------------------------------------------------
-template <typename T, int V, int OP, bool GATHER, bool PACKED>
-__global__ void __launch_bounds__(kRedThreads, Store<T>::kMinBlocks)
-segreduce_kernel(const T* __restrict__ data, const int64_t* __restrict__ ridx, const int64_t* __restrict__ off,
-                 int64_t N, int64_t S, int64_t H, int R, T* __restrict__ out, typename Store<T>::Acc* __restrict__ head,
-                 typename Store<T>::Acc* __restrict__ tail, int64_t* __restrict__ tail_seg, RedHeader* hdr,
-                 int lanes_log2, int64_t chunks) {
-  using A = typename Store<T>::Acc;
-  constexpr bool kFast = sizeof(T) == 2;  // 16-bit storage: 1e-2 tolerance, approximate exp is plenty
-  constexpr int P = OpInfo<OP>::kParts;
-  // 2^lanes_log2 threads span one row (16 bytes each).  Rows of >= 32 vectors: that is the whole CTA (one chunk per
-  // CTA, boundaries CTA-uniform).  Shorter rows (32 .. 256 bytes): the CTA hosts blockDim / lanes chunks side by
-  // side, one per thread group, so that no lane idles; groups of a warp then diverge at their own boundaries.
-  // (a compile-time switch: the extra index arithmetic made the wide-row logsumexp instance spill at its 80 registers)
-  const int lanes = PACKED ? 1 << lanes_log2 : (int)blockDim.x;
-  const int64_t chunk = PACKED ? (int64_t)blockIdx.x * (blockDim.x >> lanes_log2) + (threadIdx.x >> lanes_log2) : (int64_t)blockIdx.x;
-  const int64_t col = PACKED ? ((int64_t)blockIdx.y * lanes + (threadIdx.x & (lanes - 1))) * V
-                             : ((int64_t)blockIdx.y * blockDim.x + threadIdx.x) * V;
-  const bool active = PACKED ? (col < H && chunk < chunks) : col < H;
-  const int64_t row0 = (!PACKED || chunk < chunks) ? chunk * R : N;
-  const int64_t row1 = row0 + R < N ? row0 + R : N;
+}  // namespace rua
 
-  GlobalOff g{off};
-  int64_t s = owner_search(g, S, (!PACKED || row0 < N) ? row0 : (N > 0 ? N - 1 : 0));
-  int64_t seg_beg = __ldg(off + s), seg_end = __ldg(off + s + 1);
-  bool open = seg_beg < row0;   // the segment began in an earlier chunk
-  bool pending = false;
+#include "reduce_kernel.cuh"
 
-  State<A, V, OP> st;
-  st.reset();
-  A ext = OP == RUA_MIN ? -inf_of<A>() : inf_of<A>();
-  uint32_t ext2[4] = {Pk<T>::kPosInf, Pk<T>::kPosInf, Pk<T>::kPosInf, Pk<T>::kPosInf};  // packed running min
-  bool saw_nan = false;
-
-  const T* colp = data + col;
-  for (int64_t r = row0; r < row1; r += kRedUnroll) {
-    Raw<T, V> raw[kRedUnroll];
-    if (active) {
-#pragma unroll
-      for (int k = 0; k < kRedUnroll; ++k)
-        if (r + k < row1) load_raw<T, V>(colp + (GATHER ? __ldg(ridx + r + k) : r + k) * H, raw[k]);  // compile-time: row gather (scatter_*)
-    }
-    // the current segment ends after row `seg_end - 1`: store it and move to the next non-empty one
-    auto finish_segment = [&]() {
-      if (active) {
-        if (open) {
-          store_partial<A, V, OP>(head + chunk * P * H, H, col, st);
-        } else {
-          A o[V];
-          st.finalize(seg_end - seg_beg, o);
-          if (OpInfo<OP>::kNeedsExt) saw_nan |= st.any_nan_out(o);
-          store_vec<T, V>(out + s * H + col, o);
-        }
-      }
-      st.reset();
-      open = false;
-      pending = false;
-      do {
-        ++s;
-        seg_beg = seg_end;
-        seg_end = s < S ? __ldg(off + s + 1) : (int64_t)0x7fffffffffffffffll;
-      } while (s < S && seg_end == seg_beg);
-    };
-
-    // Walk the batch run by run: rows [k, e) of the batch belong to the current segment.  Register
-    // arrays need static indices, so the per-row code is an unrolled, range-predicated sweep; the
-    // (large) segment-finalising code appears once per kernel instead of once per unrolled row.
-    const int nrows = (int)(row1 - r < kRedUnroll ? row1 - r : kRedUnroll);
-    int k = 0;
-    while (k < nrows) {
-      const int64_t left_in_seg = seg_end - r;
-      const int e = (int)(left_in_seg < nrows ? left_in_seg : nrows);
-      bool done = false;
-      if constexpr (OpInfo<OP>::kIsLse) {
-        if (k == 0 && e == kRedUnroll) {
-          // fast path (uniform): all 8 rows belong to the current segment.  Batch max first, one rescale
-          // of the running sum, then exactly one FFMA + EX2 + FADD per element; for 16-bit storage the
-          // max and the global-extreme tracking run on packed pairs (HMNMX2), halving their issue cost.
-          if (active) lse_batch<T, V, kRedUnroll>(raw, st.a, st.s, ext, ext2);
-          done = true;
-        }
-        // (round 2: batches of 4 rows / 64 registers / 8 CTAs per SM instead of 8 rows / 80 registers / 6 CTAs measured
-        // 79.2 % of peak at cfg3 against 85.2 %: the kernel is bound by issue slots and the MUFU pipe -- one EX2 per
-        // element is 1.46 ms of SFU time at 16 per clock per SM inside a 2.4 ms kernel -- not by exposed latency.)
-        // (round 2: a masked batched form for boundary batches -- rows [k, e) only -- measured 81.3 % of peak at cfg3
-        // against 84.6 % for the per-element update below: the kernel sits at its 80-register cap and the extra code
-        // costs more than the ~13 % of rows it would speed up.  Dropped.)
-      }
-      if (!done && active) {
-#pragma unroll
-        for (int kk = 0; kk < kRedUnroll; ++kk) {
-          if (kk >= k && kk < e) {
-            A x[V];
-            unpack_raw<T, V>(raw[kk], x);
-            st.template add<kFast>(x);
-            if (OpInfo<OP>::kNeedsExt) {
-#pragma unroll
-              for (int v = 0; v < V; ++v) ext = OP == RUA_MIN ? max_num(ext, x[v]) : min_num(ext, x[v]);
-            }
-          }
-        }
-      }
-      pending = true;
-      k = e;
-      if (r + e == seg_end) finish_segment();  // uniform across the CTA
-    }
-  }
-  if (OpInfo<OP>::kIsLse) ext = min_num(ext, packed_min_to_acc<T, V>(ext2));
-  // tell the span kernel which segment (if any) starts in this chunk and runs past its end
-  if ((PACKED ? ((threadIdx.x & (lanes - 1)) == 0 && chunk < chunks) : threadIdx.x == 0) && blockIdx.y == 0)
-    tail_seg[chunk] = (pending && !open) ? s : -1;
-  if (pending && active) {
-    // the segment continues in the next chunk: whole-chunk pieces go to `head`, suffix pieces to `tail`
-    store_partial<A, V, OP>((open ? head : tail) + chunk * P * H, H, col, st);
-    if (OpInfo<OP>::kNeedsExt) {
-#pragma unroll
-      for (int v = 0; v < V; ++v) saw_nan |= (st.a[v] != st.a[v]);
-    }
-  }
-
-  if (OpInfo<OP>::kNeedsExt) {
-    __shared__ unsigned long long s_key[kRedThreads / 32];
-    __shared__ int s_nan;
-    if (threadIdx.x == 0) s_nan = 0;
-    __syncthreads();
-    unsigned long long key = order_key(ext);
-#pragma unroll
-    for (int d = 16; d > 0; d >>= 1) {
-      unsigned long long o = __shfl_xor_sync(kFullMask, key, d);
-      key = OP == RUA_MIN ? (o > key ? o : key) : (o < key ? o : key);
-    }
-    if ((threadIdx.x & 31) == 0) s_key[threadIdx.x >> 5] = key;
-    if (saw_nan) s_nan = 1;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-      for (int w = 1; w < (int)(blockDim.x >> 5); ++w) {
-        unsigned long long o = s_key[w];
-        key = OP == RUA_MIN ? (o > key ? o : key) : (o < key ? o : key);
-      }
-      if (OP == RUA_MIN) atomicMax(&hdr->ext_key, key); else atomicMin(&hdr->ext_key, key);
-      if (s_nan) atomicOr(&hdr->nan_flag, 1u);
-    }
-  }
-}
+namespace rua {
 
 // combine the pieces of every segment that crosses a chunk boundary, in chunk order
 template <typename T, int V, int OP>
@@ -208,25 +72,27 @@ segreduce_span_kernel(const int64_t* __restrict__ off, int64_t N, int64_t S, int
     if (end <= (c + 1) * R) break;
   }
   A o[V];
-  acc.finalize(end - beg, o);
+  acc.template finalize<kFast>(end - beg, o);
   if (OpInfo<OP>::kNeedsExt && acc.any_nan_out(o)) atomicOr(&hdr->nan_flag, 1u);
   store_vec<T, V>(out + s * H + col, o);
 }
 
-// empty segments and NaN poisoning (reference `initial` semantics, reduce.py:35,40,57-61)
+// empty segments and NaN poisoning (reference `initial` semantics, reduce.py:35,40,57-61).  A lane tests one segment
+// (coalesced offset loads: S threads, not S x H / V -- with sub-word pooling S is 40 % of N and the old one-thread-per-
+// output-vector form cost a fifth of the whole reduction); the rows that do need a value are then filled by the whole warp.
 template <typename T, int V, int OP>
 __global__ void __launch_bounds__(256)
 segreduce_patch_kernel(const int64_t* __restrict__ off, int64_t S, int64_t H, T* __restrict__ out,
                        const RedHeader* __restrict__ hdr) {
   using A = typename Store<T>::Acc;
-  const int64_t hv = H / V;
-  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= S * hv) return;
-  const int64_t s = idx / hv;
-  const int64_t col = (idx - s * hv) * V;
+  const int lane = threadIdx.x & 31;
+  const int64_t s0 = (((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5) * 32;
+  if (s0 >= S) return;                                   // warp-uniform
   const bool poison = OpInfo<OP>::kNeedsExt && hdr->nan_flag != 0;
-  const bool empty = __ldg(off + s + 1) == __ldg(off + s);
-  if (!poison && !empty) return;
+  const int64_t s = s0 + lane;
+  const bool flag = s < S && (poison || __ldg(off + s + 1) == __ldg(off + s));
+  unsigned todo = __ballot_sync(kFullMask, flag);
+  if (todo == 0u) return;
   A val;
   if (poison) val = nan_of<A>();
   else if (OP == RUA_SUM || OP == RUA_MEAN) val = A(0);
@@ -235,7 +101,17 @@ segreduce_patch_kernel(const int64_t* __restrict__ off, int64_t S, int64_t H, T*
   A o[V];
 #pragma unroll
   for (int v = 0; v < V; ++v) o[v] = val;
-  store_vec<T, V>(out + s * H + col, o);
+  const int64_t hv = H / V;
+  if (hv == 1) {                                         // one vector per row: every lane fills its own segment
+    if (flag) store_vec<T, V>(out + s * H, o);
+    return;
+  }
+  while (todo) {
+    const int b = __ffs(todo) - 1;
+    todo &= todo - 1u;
+    T* row = out + (s0 + b) * H;
+    for (int64_t c = lane; c < hv; c += 32) store_vec<T, V>(row + c * V, o);
+  }
 }
 
 __global__ void segreduce_init_kernel(RedHeader* hdr, int is_min) {
@@ -319,7 +195,7 @@ static int run_reduce(const RedPlan& p, const void* data, const int64_t* ridx, c
     // empty segments of sum / mean / prod are written inline, so only max / min / logsumexp need the patch pass
     if ((rc = warpseg_launch(p.dtype, H, OP, data, off, N, S, out, hdr, st))) return rc;
     if (!OpInfo<OP>::kNeedsExt) return RUA_OK;
-    segreduce_patch_kernel<T, V, OP><<<(unsigned)ceil_div(S * (H / V), 256), 256, 0, st>>>(off, S, H, (T*)out, hdr);
+    segreduce_patch_kernel<T, V, OP><<<(unsigned)ceil_div(S, 256), 256, 0, st>>>(off, S, H, (T*)out, hdr);
     return check_launch();
   }
   if (N > 0) {
@@ -334,7 +210,11 @@ static int run_reduce(const RedPlan& p, const void* data, const int64_t* ridx, c
                                                                       head, tail, tail_seg, hdr, p.lanes_log2, p.chunks)
       const bool packed = (p.main_threads >> p.lanes_log2) > 1;
       if constexpr (V > 1) {   // packing exists for the vectorised instances only (V = 1 is the odd-alignment fallback)
-        if (packed) { if (ridx) RUA_LAUNCH_SEGREDUCE(true, true); else RUA_LAUNCH_SEGREDUCE(false, true); }
+        if (short_applies(N, S, OP)) {
+          rc = short_launch(p.dtype, OP, ridx != nullptr, packed, grid, p.main_threads, data, ridx, off, N, S, H, p.R, out,
+                            head, tail, tail_seg, hdr, p.lanes_log2, p.chunks, st);
+          if (rc) return rc;
+        } else if (packed) { if (ridx) RUA_LAUNCH_SEGREDUCE(true, true); else RUA_LAUNCH_SEGREDUCE(false, true); }
         else { if (ridx) RUA_LAUNCH_SEGREDUCE(true, false); else RUA_LAUNCH_SEGREDUCE(false, false); }
       } else {
         if (ridx) RUA_LAUNCH_SEGREDUCE(true, false); else RUA_LAUNCH_SEGREDUCE(false, false);
@@ -348,8 +228,7 @@ static int run_reduce(const RedPlan& p, const void* data, const int64_t* ridx, c
       if ((rc = check_launch())) return rc;
     }
   }
-  int64_t total = S * (H / V);
-  segreduce_patch_kernel<T, V, OP><<<(unsigned)ceil_div(total, 256), 256, 0, st>>>(off, S, H, (T*)out, hdr);
+  segreduce_patch_kernel<T, V, OP><<<(unsigned)ceil_div(S, 256), 256, 0, st>>>(off, S, H, (T*)out, hdr);
   return check_launch();
 }
 

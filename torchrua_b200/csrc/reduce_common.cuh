@@ -118,10 +118,27 @@ template <> __device__ __forceinline__ double inf_of<double>() { return CUDART_I
 template <typename A> __device__ __forceinline__ A nan_of();
 template <> __device__ __forceinline__ float nan_of<float>() { return CUDART_NAN_F; }
 template <> __device__ __forceinline__ double nan_of<double>() { return CUDART_NAN; }
-template <bool kFast> __device__ __forceinline__ float exp_acc(float x) { return kFast ? __expf(x) : expf(x); }
+__device__ __forceinline__ float ex2_approx(float x) {
+  float r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+__device__ __forceinline__ float lg2_approx(float x) {
+  float r;
+  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+// kFast (16-bit storage, 1e-2 contract): one FMUL + one MUFU.  (__expf / __logf are the non-ftz forms: they wrap the
+// MUFU in a denormal range check and two rescaling multiplies -- 4-5 instructions per call, which the per-row update
+// of short-segment logsumexp pays per element.)
+template <bool kFast> __device__ __forceinline__ float exp_acc(float x) {
+  return kFast ? ex2_approx(x * 1.4426950408889634f) : expf(x);
+}
 template <bool kFast> __device__ __forceinline__ double exp_acc(double x) { return exp(x); }
-__device__ __forceinline__ float log_acc(float x) { return logf(x); }
-__device__ __forceinline__ double log_acc(double x) { return log(x); }
+template <bool kFast = false> __device__ __forceinline__ float log_acc(float x) {
+  return kFast ? lg2_approx(x) * 0.6931471805599453f : logf(x);
+}
+template <bool kFast = false> __device__ __forceinline__ double log_acc(double x) { return log(x); }
 __device__ __forceinline__ float abs_acc(float x) { return fabsf(x); }
 __device__ __forceinline__ double abs_acc(double x) { return fabs(x); }
 
@@ -223,11 +240,6 @@ __device__ __forceinline__ typename Store<T>::Acc packed_min_to_acc(const uint32
   return m;
 }
 
-__device__ __forceinline__ float ex2_approx(float x) {
-  float r;
-  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
-  return r;
-}
 
 // logsumexp over kRows rows that all belong to the current segment: a[] = running max, s[] = running
 // sum of exp(x - a).  One EX2 per element (plus one per column for the rescale).
@@ -369,12 +381,26 @@ struct State {
       }
     }
   }
+  // kFast (16-bit storage): lg2.approx instead of the ~25-instruction logf -- with segments of a few rows the logarithm
+  // of every OUTPUT element was a third of all instructions of the kernel
+  template <bool kFast = false>
   __device__ __forceinline__ void finalize(int64_t len, A* out) const {
 #pragma unroll
     for (int v = 0; v < V; ++v) {
       if (OP == RUA_MEAN) out[v] = (a[v] != a[v]) ? a[v] : a[v] / (A)len;
-      else if (OP == RUA_LOGSUMEXP) out[v] = log_acc(s[v]) + a[v];
+      else if (OP == RUA_LOGSUMEXP) out[v] = log_acc<kFast>(s[v]) + a[v];
       else out[v] = a[v];
+    }
+  }
+  // 16-bit storage, very short segments: one reciprocal per segment instead of a division per element (the result is
+  // rounded to 8 / 11 mantissa bits afterwards; the 1e-2 contract of DESIGN.md section 4 has four decimal digits to spare)
+  __device__ __forceinline__ void finalize_recip(int64_t len, A* out) const {
+    if (OP == RUA_MEAN) {
+      const A inv = A(1) / (A)len;
+#pragma unroll
+      for (int v = 0; v < V; ++v) out[v] = a[v] * inv;
+    } else {
+      finalize<true>(len, out);
     }
   }
   __device__ __forceinline__ bool any_nan_out(const A* out) const {

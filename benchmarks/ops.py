@@ -218,6 +218,10 @@ def cfg2(results, reps, quiet=False, light=False):
     bwd(lambda: rua.segment_max(leaf, lc), 3 * nd + 2 * b * d, 'bwd segment_max',
         lambda: torch.segment_reduce(leaf, 'max', lengths=lc, unsafe=True))
     bwd(lambda: rua.segment_logsumexp(leaf, lc), 2 * nd + 2 * b * d, 'bwd segment_logsumexp')
+    # the same on sub-word pieces (segments of 1..4 rows)
+    bwd(lambda: rua.segment_mean(leaf, short), nd + s_short * d, 'bwd segment_mean (pieces U[1,4])',
+        lambda: torch.segment_reduce(leaf, 'mean', lengths=short, unsafe=True))
+    bwd(lambda: rua.segment_max(leaf, short), 2 * nd + 2 * s_short * d, 'bwd segment_max (pieces U[1,4])')   # ties counted in-kernel: data read once
 
 
 def cfg3(results, reps, quiet=False):

@@ -446,3 +446,27 @@ def test_cfg5_index_only_properties(rua):
     assert m.shape == (1_000_000, 64) and torch.equal(m.sum(1).cpu(), lens)
     left = c.left(-1)
     assert torch.equal(left.idx().data.cpu(), torch.nonzero(m.view(-1).cpu()).view(-1))
+
+
+@pytest.mark.parametrize('fn', ['max', 'min'])
+@pytest.mark.parametrize('feat,dtype', [((8,), torch.float32), ((256,), torch.float32), ((64,), torch.float64), ((5,), torch.float32)])
+def test_segment_extreme_backward_ties(rua, fn, feat, dtype):
+    """max / min backward with MANY ties (small-integer data): segments inside one chunk are counted by the thread that
+    writes their gradient, segments crossing chunk boundaries through the per-chunk counters (csrc/reduce_bwd.cu);
+    both against torch autograd of amax / amin per segment (even split among ties, like SegmentReduceBackward0)."""
+    rng = np.random.default_rng(17)
+    sizes = np.concatenate([rng.integers(0, 5, 300), [700, 1, 0, 333], rng.integers(1, 4, 200), [130]]).astype(np.int64)
+    n = int(sizes.sum())
+    x = torch.randint(0, 3, (n,) + feat, generator=torch.Generator().manual_seed(8)).to(dtype)
+    dense = (lambda p: p.amax(0)) if fn == 'max' else (lambda p: p.amin(0))
+    rleaf = x.clone().requires_grad_(True)
+    pieces = [dense(p) if p.shape[0] else torch.zeros(feat, dtype=dtype) for p in torch.split(rleaf, sizes.tolist())]
+    rout = torch.stack(pieces)
+    w = torch.randn(rout.shape, generator=torch.Generator().manual_seed(9)).to(dtype)
+    w[torch.from_numpy(sizes == 0)] = 0            # empty segments: the reference's `initial` value, no gradient
+    (rout * w).sum().backward()
+    leaf = x.cuda().requires_grad_(True)
+    out = getattr(rua, 'segment_' + fn)(leaf, torch.from_numpy(sizes).cuda())
+    (out * w.cuda()).sum().backward()
+    tol = 1e-12 if dtype == torch.float64 else 1e-6
+    np.testing.assert_allclose(host(leaf.grad), host(rleaf.grad), rtol=tol, atol=tol)

@@ -36,6 +36,9 @@ def timed(fn, reps=9):
     return statistics.median(ts)
 
 
+ONLY = set(sys.argv[2].split(',')) if len(sys.argv) > 2 else None      # e.g. 'bwd max,seg_max'
+
+
 def main():
     out = []
     print(f'{"row bytes":>9} {"B":>8} {"N":>10} | ' + ' | '.join(f'{k:>14}' for k in ('C->P', 'P->C', 'C->L', 'L->C', 'C.rev', 'seg_sum', 'seg_max', 'seg_lse', 'bwd sum', 'bwd max')))
@@ -64,13 +67,15 @@ def main():
                                  ('seg_max', lambda: rua.segment_max(data, c.token_sizes), nd + b * row),
                                  ('seg_lse', lambda: rua.segment_logsumexp(data, c.token_sizes), nd + b * row),
                                  ('bwd sum', bwd('sum'), nd + b * row), ('bwd max', bwd('max'), 3 * nd + 2 * b * row)):
+            if ONLY and name not in ONLY:
+                continue
             ms = timed(fn)
             res[name] = {'ms': ms, 'GBs': nbytes / ms / 1e6, 'frac': nbytes / ms / 1e6 / PEAK}
         out.append({'row_bytes': row, 'B': b, 'N': n, 'ops': res})
         print(f'{row:>9} {b:>8} {n:>10} | ' + ' | '.join(f"{r['GBs']:7.0f} ({100 * r['frac']:3.0f}%)" for r in res.values()), flush=True)
         del data, c, p, left, leaf
         _native._CACHE.clear()
-    if len(sys.argv) > 1:
+    if len(sys.argv) > 1 and sys.argv[1] != '-':
         json.dump(out, open(sys.argv[1], 'w'), indent=1)
 
 

@@ -8,10 +8,12 @@
 //   logsumexp : g[s] * exp(x - out[s])        (m is detached in the reference, so this is exact)
 // Same decomposition as the forward pass: fixed row chunks x 128 column vectors per CTA, segment
 // boundaries uniform across the CTA, 16-byte coalesced loads/stores along H.  max/min need the tie
-// counts first.  A segment that lies inside one chunk (every short segment: sub-word pooling) is counted by the thread
-// that owns it right before it writes the gradient -- a second look at rows that are still in L1, no atomics, no
-// count array; only segments that CROSS a chunk boundary go through a count pass with integer atomics (order
-// independent => deterministic) into one slot per chunk: at most one crossing segment starts in any chunk.
+// counts first: one extra read of the data with integer atomics (order independent => deterministic).
+// Batches of very short segments (sub-word pieces: N <= 8 S) use the INLINE instances instead: a segment that lies inside
+// one chunk is counted by the thread that owns it right before it writes the gradient (a second look at rows that are
+// still in L1: no atomics, no S x H counter array to clear, fill and read back), and only segments that CROSS a chunk
+// boundary go through the count pass, into one slot of H counters per chunk (at most one crossing segment starts in
+// any chunk).  Kept as separate instances: folded into one kernel the extra code cost the long-segment case 5-25 %.
 #include "reduce_common.cuh"
 
 namespace rua {
@@ -23,6 +25,7 @@ int warpseg_bwd_launch(int32_t dtype, int64_t H, int32_t op, const void* gout, c
                        const int64_t* off, int64_t N, int64_t S, void* grad, cudaStream_t st);
 
 constexpr int kBwdUnroll = 4;
+constexpr int kTieInlineAvg = 8;   // max / min backward: average segment length up to which the INLINE instances run
 
 template <typename T, int V>
 __device__ __forceinline__ void load_acc(const T* p, typename Store<T>::Acc* x) {
@@ -57,18 +60,18 @@ struct SegCursor {
   __device__ __forceinline__ bool valid() const { return s < S; }
 };
 
+// INLINE instance: only the chunk-crossing segments, counters keyed by the chunk the segment starts in
 template <typename T, int V, int OP>
 __global__ void __launch_bounds__(kRedThreads)
-tie_count_kernel(const T* __restrict__ data, const T* __restrict__ out, const int64_t* __restrict__ off, int64_t N,
-                 int64_t S, int64_t H, int R_log2, int* __restrict__ counts, int lanes_log2) {
+tie_count_crossing_kernel(const T* __restrict__ data, const T* __restrict__ out, const int64_t* __restrict__ off, int64_t N,
+                          int64_t S, int64_t H, int R, int* __restrict__ counts, int lanes_log2) {
   using A = typename Store<T>::Acc;
-  // 2^lanes_log2 threads span one row; short rows: the CTA hosts several chunks side by side (see reduce.cu)
   const int lanes = 1 << lanes_log2;
   const int64_t chunk = (int64_t)blockIdx.x * (blockDim.x >> lanes_log2) + (threadIdx.x >> lanes_log2);
   const int64_t col = ((int64_t)blockIdx.y * lanes + (threadIdx.x & (lanes - 1))) * V;
-  const int64_t row0 = chunk << R_log2;
+  const int64_t row0 = chunk * R;
   const bool active = col < H && row0 < N;
-  const int64_t row1 = row0 + (1ll << R_log2) < N ? row0 + (1ll << R_log2) : N;
+  const int64_t row1 = row0 + R < N ? row0 + R : N;
   if (row0 >= N) return;
   SegCursor cur;
   cur.init(off, S, row0);
@@ -77,32 +80,73 @@ tie_count_kernel(const T* __restrict__ data, const T* __restrict__ out, const in
     cur.seek(row);
     if (!cur.valid()) break;
     const int64_t lo = cur.beg > row0 ? cur.beg : row0, hi = cur.end < row1 ? cur.end : row1;
-    if (cur.beg < row0 || cur.end > row1) {          // crosses a chunk boundary: this chunk's share of its ties
-      if (active) {
-        A o[V];
-        int cnt[V];
-        load_acc<T, V>(out + cur.s * H + col, o);
+    if ((cur.beg < row0 || cur.end > row1) && active) {      // this chunk's share of a crossing segment's ties
+      A o[V];
+      int cnt[V];
+      load_acc<T, V>(out + cur.s * H + col, o);
 #pragma unroll
-        for (int v = 0; v < V; ++v) cnt[v] = 0;
-        for (int64_t q = lo; q < hi; ++q) {
-          A x[V];
-          load_acc<T, V>(data + q * H + col, x);
+      for (int v = 0; v < V; ++v) cnt[v] = 0;
+      for (int64_t q = lo; q < hi; ++q) {
+        A x[V];
+        load_acc<T, V>(data + q * H + col, x);
 #pragma unroll
-          for (int v = 0; v < V; ++v) cnt[v] += (x[v] != x[v] || x[v] == o[v]) ? 1 : 0;
-        }
-        int* slot = counts + (cur.beg >> R_log2) * H + col;      // keyed by the chunk the segment starts in
-#pragma unroll
-        for (int v = 0; v < V; ++v) if (cnt[v]) atomicAdd(slot + v, cnt[v]);
+        for (int v = 0; v < V; ++v) cnt[v] += (x[v] != x[v] || x[v] == o[v]) ? 1 : 0;
       }
+      int* slot = counts + (cur.beg / R) * H + col;
+#pragma unroll
+      for (int v = 0; v < V; ++v) if (cnt[v]) atomicAdd(slot + v, cnt[v]);
     }
-    row = hi;                                          // segments inside the chunk are counted by the backward kernel itself
+    row = hi;                                                // segments inside the chunk: counted by the gradient kernel
   }
 }
 
 template <typename T, int V, int OP>
 __global__ void __launch_bounds__(kRedThreads)
+tie_count_kernel(const T* __restrict__ data, const T* __restrict__ out, const int64_t* __restrict__ off, int64_t N,
+                 int64_t S, int64_t H, int R, int* __restrict__ counts, int lanes_log2) {
+  using A = typename Store<T>::Acc;
+  // 2^lanes_log2 threads span one row; short rows: the CTA hosts several chunks side by side (see reduce.cu)
+  const int lanes = 1 << lanes_log2;
+  const int64_t chunk = (int64_t)blockIdx.x * (blockDim.x >> lanes_log2) + (threadIdx.x >> lanes_log2);
+  const int64_t col = ((int64_t)blockIdx.y * lanes + (threadIdx.x & (lanes - 1))) * V;
+  const int64_t row0 = chunk * R;
+  const bool active = col < H && row0 < N;
+  const int64_t row1 = row0 + R < N ? row0 + R : N;
+  if (row0 >= N) return;
+  SegCursor cur;
+  cur.init(off, S, row0);
+  A o[V];
+  int cnt[V];
+#pragma unroll
+  for (int v = 0; v < V; ++v) cnt[v] = 0;
+  if (active && cur.valid()) load_acc<T, V>(out + cur.s * H + col, o);
+  for (int64_t row = row0; row < row1; ++row) {
+    int64_t prev = cur.s;
+    if (cur.seek(row)) {
+      if (active) {
+#pragma unroll
+        for (int v = 0; v < V; ++v) { if (cnt[v]) atomicAdd(counts + prev * H + col + v, cnt[v]); cnt[v] = 0; }
+        if (cur.valid()) load_acc<T, V>(out + cur.s * H + col, o);
+      }
+    }
+    if (!cur.valid()) break;
+    if (active) {
+      A x[V];
+      load_acc<T, V>(data + row * H + col, x);
+#pragma unroll
+      for (int v = 0; v < V; ++v) cnt[v] += (x[v] != x[v] || x[v] == o[v]) ? 1 : 0;
+    }
+  }
+  if (active && cur.valid()) {
+#pragma unroll
+    for (int v = 0; v < V; ++v) if (cnt[v]) atomicAdd(counts + cur.s * H + col + v, cnt[v]);
+  }
+}
+
+template <typename T, int V, int OP, bool INLINE = false>
+__global__ void __launch_bounds__(kRedThreads)
 segreduce_bwd_kernel(const T* __restrict__ gout, const T* __restrict__ out, const T* __restrict__ data,
-                     const int64_t* __restrict__ off, int64_t N, int64_t S, int64_t H, int R_log2,
+                     const int64_t* __restrict__ off, int64_t N, int64_t S, int64_t H, int R,
                      T* __restrict__ grad, const int* __restrict__ counts, int lanes_log2) {
   using A = typename Store<T>::Acc;
   constexpr bool kNeedsX = OP == RUA_MAX || OP == RUA_MIN || OP == RUA_PROD || OP == RUA_LOGSUMEXP;
@@ -110,9 +154,9 @@ segreduce_bwd_kernel(const T* __restrict__ gout, const T* __restrict__ out, cons
   const int lanes = 1 << lanes_log2;
   const int64_t chunk = (int64_t)blockIdx.x * (blockDim.x >> lanes_log2) + (threadIdx.x >> lanes_log2);
   const int64_t col = ((int64_t)blockIdx.y * lanes + (threadIdx.x & (lanes - 1))) * V;
-  const int64_t row0 = chunk << R_log2;
+  const int64_t row0 = chunk * R;
   if (col >= H || row0 >= N) return;
-  const int64_t row1 = row0 + (1ll << R_log2) < N ? row0 + (1ll << R_log2) : N;
+  const int64_t row1 = row0 + R < N ? row0 + R : N;
   SegCursor cur;
   cur.init(off, S, row0);
   A g[V], o[V], c[V];
@@ -125,26 +169,34 @@ segreduce_bwd_kernel(const T* __restrict__ gout, const T* __restrict__ out, cons
       for (int v = 0; v < V; ++v) g[v] *= inv;
     }
     if (OP == RUA_MAX || OP == RUA_MIN) {
-      int n[V];
-      if (cur.end - cur.beg == 1) {                    // a single row is its own extreme
+      if constexpr (INLINE) {
+        int n[V];
+        if (cur.end - cur.beg == 1) {                  // a single row is its own extreme
 #pragma unroll
-        for (int v = 0; v < V; ++v) n[v] = 1;
-      } else if (cur.beg >= row0 && cur.end <= row1) {
-        // inside this chunk: count the ties here (the rows are read again by the loop below a moment later: L1 hits)
+          for (int v = 0; v < V; ++v) n[v] = 1;
+        } else if (cur.beg >= row0 && cur.end <= row1) {
+          // inside this chunk: count the ties here (the loop below reads the same rows again a moment later: L1 hits)
 #pragma unroll
-        for (int v = 0; v < V; ++v) n[v] = 0;
-        for (int64_t q = cur.beg; q < cur.end; ++q) {
-          A x[V];
-          load_acc<T, V>(data + q * H + col, x);
+          for (int v = 0; v < V; ++v) n[v] = 0;
+          for (int64_t q = cur.beg; q < cur.end; ++q) {
+            A x[V];
+            load_acc<T, V>(data + q * H + col, x);
 #pragma unroll
-          for (int v = 0; v < V; ++v) n[v] += (x[v] != x[v] || x[v] == o[v]) ? 1 : 0;
+            for (int v = 0; v < V; ++v) n[v] += (x[v] != x[v] || x[v] == o[v]) ? 1 : 0;
+          }
+        } else {
+#pragma unroll
+          for (int v = 0; v < V; ++v) n[v] = counts[(cur.beg / R) * H + col + v];
         }
+#pragma unroll
+        for (int v = 0; v < V; ++v) c[v] = n[v] > 1 ? g[v] / (A)n[v] : g[v];
       } else {
 #pragma unroll
-        for (int v = 0; v < V; ++v) n[v] = counts[(cur.beg >> R_log2) * H + col + v];
+        for (int v = 0; v < V; ++v) {
+          int n = counts[cur.s * H + col + v];
+          c[v] = n > 1 ? g[v] / (A)n : g[v];
+        }
       }
-#pragma unroll
-      for (int v = 0; v < V; ++v) c[v] = n[v] > 1 ? g[v] / (A)n[v] : g[v];
     }
   };
   if (cur.valid()) load_seg();
@@ -193,49 +245,41 @@ segreduce_bwd_kernel(const T* __restrict__ gout, const T* __restrict__ out, cons
   }
 }
 
-struct BwdPlan {
-  int threads, lanes_log2, R_log2;
-  int64_t col_tiles, chunks;
-};
-
-static BwdPlan plan_bwd(int64_t N, int64_t H, int V) {
-  BwdPlan p;
-  const int64_t hv = H / V;
+template <typename T, int V, int OP>
+static int run_bwd(const void* gout, const void* out, const void* data, const int64_t* off, int64_t N, int64_t S,
+                   int64_t H, void* grad, void* ws, cudaStream_t st) {
+  int64_t hv = H / V;
   int threads = 32;
   while (threads < kRedThreads && threads < hv) threads <<= 1;
-  p.col_tiles = ceil_div(hv, threads);
+  int64_t col_tiles = ceil_div(hv, threads);
+  if (col_tiles > 65535) return RUA_ERR_UNSUPPORTED;
   int lanes = threads;
   if (hv < 32) { lanes = 1; while (lanes < hv) lanes <<= 1; threads = kRedThreads; }   // short rows: chunks side by side
   int lg = 0;
   while ((1 << lg) < lanes) ++lg;
   const int cpc = threads / lanes;
-  int rl = 7;                                       // chunks of 128 rows, down to 16 while the grid is small
-  while (rl > 4 && ceil_div(ceil_div(N, (int64_t)1 << rl), cpc) * p.col_tiles < (int64_t)kNumSMs * 8) --rl;
-  p.threads = threads;
-  p.lanes_log2 = lg;
-  p.R_log2 = rl;
-  p.chunks = ceil_div(N, (int64_t)1 << rl);
-  return p;
-}
-
-template <typename T, int V, int OP>
-static int run_bwd(const void* gout, const void* out, const void* data, const int64_t* off, int64_t N, int64_t S,
-                   int64_t H, void* grad, void* ws, cudaStream_t st) {
-  const BwdPlan p = plan_bwd(N, H, V);
-  if (p.col_tiles > 65535) return RUA_ERR_UNSUPPORTED;
-  const int cpc = p.threads >> p.lanes_log2;
-  dim3 grid((unsigned)ceil_div(p.chunks, cpc), (unsigned)p.col_tiles);
+  int R = 128;
+  while (R > 16 && ceil_div(ceil_div(N, R), cpc) * col_tiles < (int64_t)kNumSMs * 8) R >>= 1;
+  dim3 grid((unsigned)ceil_div(ceil_div(N, R), cpc), (unsigned)col_tiles);
   int rc;
   int* counts = nullptr;
-  if (OP == RUA_MAX || OP == RUA_MIN) {
-    counts = (int*)ws;                              // one slot of H counters per chunk (crossing segments only)
-    if ((rc = check_cuda(cudaMemsetAsync(counts, 0, (size_t)p.chunks * H * sizeof(int), st)))) return rc;
-    tie_count_kernel<T, V, OP><<<grid, p.threads, 0, st>>>((const T*)data, (const T*)out, off, N, S, H, p.R_log2, counts,
-                                                           p.lanes_log2);
+  if constexpr (OP == RUA_MAX || OP == RUA_MIN) {
+    counts = (int*)ws;
+    if (N <= (int64_t)kTieInlineAvg * S) {          // very short segments: ties counted inside the gradient kernel
+      const int64_t chunks = ceil_div(N, R);
+      if ((rc = check_cuda(cudaMemsetAsync(counts, 0, (size_t)chunks * H * sizeof(int), st)))) return rc;
+      tie_count_crossing_kernel<T, V, OP><<<grid, threads, 0, st>>>((const T*)data, (const T*)out, off, N, S, H, R, counts, lg);
+      if ((rc = check_launch())) return rc;
+      segreduce_bwd_kernel<T, V, OP, true><<<grid, threads, 0, st>>>((const T*)gout, (const T*)out, (const T*)data, off, N,
+                                                                     S, H, R, (T*)grad, counts, lg);
+      return check_launch();
+    }
+    if ((rc = check_cuda(cudaMemsetAsync(counts, 0, (size_t)S * H * sizeof(int), st)))) return rc;
+    tie_count_kernel<T, V, OP><<<grid, threads, 0, st>>>((const T*)data, (const T*)out, off, N, S, H, R, counts, lg);
     if ((rc = check_launch())) return rc;
   }
-  segreduce_bwd_kernel<T, V, OP><<<grid, p.threads, 0, st>>>((const T*)gout, (const T*)out, (const T*)data, off, N, S,
-                                                             H, p.R_log2, (T*)grad, counts, p.lanes_log2);
+  segreduce_bwd_kernel<T, V, OP><<<grid, threads, 0, st>>>((const T*)gout, (const T*)out, (const T*)data, off, N, S,
+                                                           H, R, (T*)grad, counts, lg);
   return check_launch();
 }
 
@@ -267,12 +311,11 @@ using namespace rua;
 extern "C" {
 
 size_t rua_segment_reduce_backward_workspace_bytes(int64_t N, int64_t S, int64_t H, int32_t dtype, int32_t op) {
-  (void)S;
-  if (op == RUA_MAX || op == RUA_MIN) {             // tie counters: H per chunk, whichever vector width the call ends up with
-    const int full = dtype == RUA_F32 ? 4 : (dtype == RUA_F64 ? 2 : 8);
-    int64_t chunks = plan_bwd(N, H, 1).chunks;
-    if (H % full == 0) { const int64_t c2 = plan_bwd(N, H, full).chunks; if (c2 > chunks) chunks = c2; }
-    return (size_t)chunks * (size_t)H * sizeof(int) + 16;
+  (void)dtype;
+  if (op == RUA_MAX || op == RUA_MIN) {
+    // tie counters: H per segment, or (very short segments) H per chunk of >= 16 rows
+    const size_t slots = N <= (int64_t)kTieInlineAvg * S ? (size_t)(N / 16 + 1) : (size_t)S;
+    return slots * (size_t)H * sizeof(int) + 16;
   }
   return 16;
 }

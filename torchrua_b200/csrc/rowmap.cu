@@ -574,10 +574,11 @@ __device__ __forceinline__ void tile_body(const RowMapParams& p, OffFn f, int64_
       }
       const int64_t j = r0 + jr;
       int64_t i, td;
-      if (is_pack) {
+      bool undescribed = false;                  // see map_row: rows of a P that poff does not describe (branch-free: a
+      if (is_pack) {                             // `continue` here cost the unrolled decode of EVERY instance 8-16 %)
         td = s;
-        if (j - base >= f(s + 1) - base) { srow[r] = kPadRow; continue; }   // see map_row: rows poff does not describe
-        i = __ldg(p.rg.sorted + (j - base));
+        undescribed = j - base >= f(s + 1) - base;
+        i = __ldg(p.rg.sorted + (undescribed ? 0 : j - base));
       } else { i = s; td = j - base; }
       int64_t sr;
       if (SRC == kGenericSrc) {
@@ -599,7 +600,7 @@ __device__ __forceinline__ void tile_body(const RowMapParams& p, OffFn f, int64_
         sr = simple_source_row<SRC>(p, i, td, base_len);
         if (SRC == RUA_CAT && sr >= p.s.rows) sr = kPadRow;   // see source_row: inconsistent lengths never read past the payload
       }
-      srow[r] = sr;
+      srow[r] = undescribed ? kPadRow : sr;
     }
   }
   V val[kTileItems];
@@ -1275,7 +1276,10 @@ static void launch_narrow(RowMapParams& p, int64_t rows, cudaStream_t st) {
     if (p.row_vecs == 1) {
       // one-vector rows: KT time tiles of 32 steps per CTA, all of their row loads in flight together
       constexpr int kMaxKT = sizeof(V) >= 16 ? 2 : 4;   // 48 KB of static shared memory
-      const int kt = gy <= 1 ? 1 : ((gy <= 2 || kMaxKT == 2) ? 2 : 4);
+      static const int kt_env = [] { const char* e = getenv("RUA_T1_KT"); return e ? atoi(e) : 0; }();
+      int kt = gy <= 1 ? 1 : ((gy <= 2 || kMaxKT == 2) ? 2 : 4);
+      if (sizeof(V) >= 16 && !from_pack) kt = 1;   // 16-byte rows into P: one tile per CTA measured 4.5 vs 4.1 TB/s (T = 512)
+      if (kt_env > 0 && kt_env <= kMaxKT) kt = kt_env;
       dim3 g1((unsigned)ceil_div(p.rg.B, 32), (unsigned)ceil_div(gy, kt));
 #define RUA_T1(FP_, KT_) row_map_transpose1_kernel<V, FP_, KT_><<<g1, 256, 0, st>>>(p)
       if (from_pack) { if (kt == 1) RUA_T1(true, 1); else if (kt == 2) RUA_T1(true, 2); else RUA_T1(true, kMaxKT); }

@@ -242,7 +242,8 @@ static int ws_launch1(int he, int op, const void* data, const int64_t* off, int6
 // enough short segments to fill the machine with warps of 32 segments each?  (host-side choice, reduce.cu)
 bool warpseg_applies(int64_t N, int64_t S) {
   static const int64_t min_s = [] { const char* e = getenv("RUA_WARPSEG_MIN_S"); return e ? atoll(e) : 32768ll; }();
-  return S >= min_s && N <= 256 * S;
+  static const int64_t max_avg = [] { const char* e = getenv("RUA_WARPSEG_MAX_AVG"); return e ? atoll(e) : 256ll; }();
+  return S >= min_s && N <= max_avg * S;
 }
 
 int warpseg_launch(int32_t dtype, int64_t H, int32_t op, const void* data, const int64_t* off, int64_t N, int64_t S,

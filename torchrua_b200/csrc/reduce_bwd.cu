@@ -160,9 +160,28 @@ segreduce_bwd_kernel(const T* __restrict__ gout, const T* __restrict__ out, cons
   SegCursor cur;
   cur.init(off, S, row0);
   A g[V], o[V], c[V];
+  // INLINE (segments of a few rows): the gradient / output rows of the NEXT segment are requested while the current one is
+  // being written -- otherwise every boundary (one per 2-3 rows) exposes a dependent DRAM load
+  Raw<T, V> next_g, next_o;
+  int64_t next_s = -1;
   auto load_seg = [&]() {
-    load_acc<T, V>(gout + cur.s * H + col, g);
-    if (kNeedsOut) load_acc<T, V>(out + cur.s * H + col, o);
+    if constexpr (INLINE) {
+      if (next_s == cur.s) {
+        unpack_raw<T, V>(next_g, g);
+        unpack_raw<T, V>(next_o, o);
+      } else {
+        load_acc<T, V>(gout + cur.s * H + col, g);
+        load_acc<T, V>(out + cur.s * H + col, o);
+      }
+      next_s = cur.s + 1;
+      if (next_s < S) {
+        load_raw<T, V>(gout + next_s * H + col, next_g);
+        load_raw<T, V>(out + next_s * H + col, next_o);
+      }
+    } else {
+      load_acc<T, V>(gout + cur.s * H + col, g);
+      if (kNeedsOut) load_acc<T, V>(out + cur.s * H + col, o);
+    }
     if (OP == RUA_MEAN) {
       A inv = A(1) / (A)(cur.end - cur.beg);
 #pragma unroll

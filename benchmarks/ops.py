@@ -145,6 +145,11 @@ def cfg2(results, reps, quiet=False, light=False):
     seg_bytes = nd + 3 * s_rows * d + 8 * s_rows          # data read, result written, result packed (read + write)
     row(results, 2, 'C.seg(8-token pieces, mean)', nd + s_rows * d + 8 * s_rows, n, lambda: c.seg(dur, rua.segment_mean), reps)
     row(results, 2, 'P.seg(8-token pieces, mean)', seg_bytes, n, lambda: srcs['P'].seg(dur, rua.segment_mean), reps)
+    left = srcs['L']
+    row(results, 2, 'L.seg(8-token pieces, mean)', nd + 8 * n + s_rows * (d + 8) + s_rows * d + b * int(dur.token_sizes.max()) * d, n,
+        lambda: left.seg(dur, rua.segment_mean), reps)
+    row(results, 2, 'L.seg unfused (reduce over all B x T rows)', btd + b * (int(dur.token_sizes.max()) + 1) * d, n,
+        lambda: left.seg(dur, lambda t_, s_: rua.segment_mean(t_, s_)), reps)
     row(results, 2, 'P.seg unfused (P->C, reduce, C->P)', seg_bytes, n,
         lambda: srcs['P'].cat().seg(dur, rua.segment_mean).pack(), reps)
     # sub-word -> word pooling: very short segments (1..4 rows of 2 KB), the common use of segment_mean / .seg

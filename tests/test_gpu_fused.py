@@ -172,3 +172,38 @@ def test_pack_seg_gradient(rua):
             (out.data * w).sum().backward()
             grads.append(x.grad)
         assert torch.allclose(grads[0], grads[1], rtol=1e-6, atol=1e-6), fn
+
+
+@pytest.mark.parametrize('feat,dtype', [((64,), torch.float32), ((256,), torch.bfloat16), ((5,), torch.float64)])
+@pytest.mark.parametrize('kind', 'LR')
+@pytest.mark.parametrize('dkind', 'CLPR')
+def test_padded_seg_gathers_real_rows_only(rua, feat, dtype, kind, dkind):
+    """L.seg / R.seg with segment_sum / mean / prod reduce the N real rows through idx() instead of all B x T rows of the
+    padded buffer (segment.py:16-28,38-50); result layout, padding values (0 / 0 / 1) and token_sizes must be what the
+    reference's composition gives -- the generic path, forced here by wrapping the reducer in a lambda."""
+    g = torch.Generator().manual_seed(21)
+    lens = torch.randperm(60, generator=g)[:37] + 1
+    data = (torch.randn((int(lens.sum()),) + feat, generator=g) * 0.3 + 1).to(dtype).cuda()
+    c = rua.C(data=data, token_sizes=lens.cuda())
+    z = build(rua, kind, c)
+    dur = build(rua, dkind, _durations(rua, lens, 5, 22))
+    for fn in ('sum', 'mean', 'prod'):
+        f = getattr(rua, 'segment_' + fn)
+        got = z.seg(dur, f)
+        want = z.seg(dur, lambda t, s, f=f: f(t, s))
+        assert type(got) is type(want) and torch.equal(got.token_sizes, want.token_sizes)
+        assert got.data.shape == want.data.shape and got.data.dtype == want.data.dtype
+        tol = {torch.float32: 1e-5, torch.float64: 1e-12, torch.bfloat16: 1e-2}[dtype]
+        assert torch.allclose(got.data.double(), want.data.double(), rtol=tol, atol=tol), fn
+    # gradient: padding rows get none, real rows what the composition gives
+    if dtype == torch.float32:
+        grads = []
+        for fused in (True, False):
+            x = z.data.detach().clone().requires_grad_(True)
+            zz = z._replace(data=x)
+            f = rua.segment_mean if fused else (lambda t, s: rua.segment_mean(t, s))
+            out = zz.seg(dur, f)
+            w = torch.randn(out.data.shape, generator=torch.Generator().manual_seed(23)).cuda()
+            (out.data * w).sum().backward()
+            grads.append(x.grad)
+        assert torch.allclose(grads[0], grads[1], rtol=1e-5, atol=1e-6)

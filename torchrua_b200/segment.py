@@ -22,7 +22,36 @@ def cat_seg(self: C, duration: Z, fn) -> C:
 C.seg = cat_seg
 
 
+# reducers whose value on an EMPTY segment is a constant (the padded positions of an L / R result are empty segments of
+# the reference's flattened reduction, segment.py:20,42): fn -> (op name, fill).  max / min / logsumexp put the global
+# extreme of the whole padded buffer there (reduce.py:35,40,57-61) and keep the generic path.
+_PADDED_FILL = {_reduce.segment_sum: ('sum', 0), _reduce.segment_mean: ('mean', 0), _reduce.segment_prod: ('prod', 1)}
+
+
+def _padded_seg_gathered(self: Z, duration: Z, fn, right: bool):
+    """L.seg / R.seg with segment_sum / mean / prod: the reference reduces all B x T rows of the padded buffer (padding
+    included, as one extra segment per row); here the reducer gathers the N real rows through `idx()` and the (few) result
+    rows are laid out left / right.  None when the generic path has to run."""
+    try:
+        hit = _PADDED_FILL.get(fn)
+    except TypeError:
+        hit = None
+    if (hit is None or not self.data.is_cuda or self.data.dtype not in _native._DTYPES or _native.STRICT_REDUCTIONS
+            or self.data.dim() < 2 or self.data.size()[1] != self.size()[1]):
+        return None
+    op, fill = hit
+    duration = duration.cat()
+    rows = self.idx().data                       # storage row of every real token, sequence-major
+    red = _native.segment_reduce_gathered(self.raw(), rows, duration.data, op)
+    out = duration._replace(data=red)
+    out = out.right(fill) if right else out.left(fill)
+    return out.data, out.token_sizes
+
+
 def _padded_seg(self: Z, duration: Z, fn, right: bool):
+    fused = _padded_seg_gathered(self, duration, fn, right)
+    if fused is not None:
+        return fused
     # one extra pad-segment per row soaks up the padding tokens (segment.py:20,42); its column is dropped
     b, t, *sizes = self.size()
     pad = (t - self.token_sizes)[:, None]

@@ -113,3 +113,17 @@ def test_tensor_indexing_still_works_after_patch():
     assert isinstance(picked, torchrua_b200.C) and picked.data.tolist() == [12, 10, 11]
     data, sizes = c                         # namedtuple unpacking
     assert c[0] is data and c[1] is sizes
+
+
+def test_seg_fast_paths_recognise_the_public_reducers():
+    """`.seg(duration, fn)` picks its gathered / short-segment paths by the identity of `fn`: the reducers exported by the
+    package AND by the alias package (`import torchrua`) must be the very functions the dispatch tables hold."""
+    import torchrua
+    import torchrua_b200
+    from torchrua_b200 import segment
+    for name in ('sum', 'mean', 'prod', 'max', 'min', 'logsumexp'):
+        fn = getattr(torchrua_b200, 'segment_' + name)
+        assert getattr(torchrua, 'segment_' + name) is fn
+        assert segment._GATHERED[fn] == name
+    assert {v[0] for v in segment._PADDED_FILL.values()} == {'sum', 'mean', 'prod'}
+    assert segment._GATHERED.get(lambda t, s: t) is None

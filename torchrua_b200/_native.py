@@ -10,6 +10,7 @@ import weakref
 from dataclasses import dataclass, field
 from typing import Optional, Tuple
 
+import numpy as np
 import torch
 from torch import Tensor
 
@@ -38,7 +39,20 @@ def require_cuda(*tensors: Tensor) -> torch.device:
     return dev
 
 
+# torch.cuda.current_stream() builds a Stream object through three layers of Python (~5 us; it used to be a third of the
+# host time of a small call, benchmarks/diag_profile.py); the raw handle is one C call.  Private but long-lived entry points
+# (inductor and triton use them); the public route stays as the fallback.
+_RAW_STREAM = getattr(torch._C, '_cuda_getCurrentRawStream', None)
+_CUR_DEVICE = getattr(torch._C, '_cuda_getDevice', None)
+if _RAW_STREAM is None or _CUR_DEVICE is None:
+    _RAW_STREAM = None
+    _CUR_DEVICE = torch.cuda.current_device
+
+
 def _stream() -> int:
+    """raw handle of the current stream of the current device"""
+    if _RAW_STREAM is not None:
+        return _RAW_STREAM(_CUR_DEVICE())
     return torch.cuda.current_stream().cuda_stream
 
 
@@ -60,7 +74,7 @@ def _on(device: torch.device):
     """device guard that costs nothing in the common one-process-per-GPU case (torch.cuda.device() is
     ~10 us of Python per use; these kernels run for 5 us)."""
     idx = device.index
-    if idx is None or idx == torch.cuda.current_device():
+    if idx is None or idx == _CUR_DEVICE():
         return _NO_GUARD
     return torch.cuda.device(device)
 
@@ -227,9 +241,10 @@ def scan(sizes: Optional[Tensor], clamp_max: int = INT64_MAX, notify: bool = Fal
                                                bs_dev.data_ptr() if tp else None, unsorted.data_ptr(), tp,
                                                base + 8 * (n + 3 + tiles), note_dev, ticket, _stream()),
                        'rua_scan_lengths_ex')
-    off, stats = buf[:n + 1], buf[n + 1:n + 3]
+    # (narrow, not slicing: Tensor.__getitem__ is patched process-wide -- as in the reference -- and costs ~2 us per use)
+    off, stats = buf.narrow(0, 0, n + 1), buf.narrow(0, n + 1, 2)
     if pack is not None:
-        return off, stats, note, buf[n + 3 + tiles:]
+        return off, stats, note, buf.narrow(0, n + 3 + tiles, n)
     if notify:
         return off, stats, note
     return off, stats
@@ -351,15 +366,15 @@ class Ragged:
                 early(self)
                 early, speculated = None, True      # at most once
             ev.synchronize()
-            n, t = int(host[0]), int(host[1])
+            n, t = host.narrow(0, 0, 2).tolist()
             if t <= cap:
                 self._spec_ok = speculated
                 break
             cap = t   # a sequence longer than the speculative cap: one more round trip, exact this time
         self._N, self._T, self.Tp = n, t, t
-        self.bs_cpu = host[2:2 + t].clone()
-        self.bs_dev = hostbuf[2:2 + t]
-        self.poff = poff[:t + 1]
+        self.bs_cpu = host.narrow(0, 2, t).clone()
+        self.bs_dev = hostbuf.narrow(0, 2, t)
+        self.poff = poff.narrow(0, 0, t + 1)
         self._keep += [hostbuf, poff]
         _cache_put(self.unsorted, 'pack', self)
         return self
@@ -384,8 +399,12 @@ def _cache_get(key_tensor: Tensor, tag: str):
     if ref() is key_tensor and key_tensor._version == version:
         made_on = getattr(value, '_stream', None)
         if made_on is not None:
-            cur = torch.cuda.current_stream(value.device)
-            if cur.cuda_stream != made_on:
+            if _RAW_STREAM is not None and value.device.index is not None:
+                same = _RAW_STREAM(value.device.index) == made_on
+            else:
+                same = torch.cuda.current_stream(value.device).cuda_stream == made_on
+            if not same:
+                cur = torch.cuda.current_stream(value.device)
                 cur.wait_stream(torch.cuda.ExternalStream(made_on, device=value.device) if made_on else
                                 torch.cuda.default_stream(value.device))
         return value
@@ -442,21 +461,29 @@ def ragged_from_pack(batch_sizes: Tensor, sorted_indices: Optional[Tensor], unso
     bs_cpu = batch_sizes.detach()
     if bs_cpu.is_cuda:
         bs_cpu = bs_cpu.cpu()
-    bs_cpu = bs_cpu.long().contiguous()
+    if bs_cpu.dtype != torch.long or not bs_cpu.is_contiguous():
+        bs_cpu = bs_cpu.long().contiguous()
     Tp = bs_cpu.numel()
-    total = int(bs_cpu.sum()) if Tp else 0
+    # [batch_sizes | poff] assembled with numpy straight in pinned memory (a handful of ~1 us calls instead of ~4 us
+    # torch ops), then ONE asynchronous H2D
+    pinned = torch.empty(2 * Tp + 1, dtype=torch.long, pin_memory=True)
+    host = pinned.numpy()
+    if Tp:
+        bs_np = bs_cpu.numpy()
+        host[:Tp] = bs_np
+        host[Tp] = 0
+        np.cumsum(bs_np, out=host[Tp + 1:])
+        total = int(host[-1])
+    else:
+        host[0] = 0
+        total = 0
     if n_rows >= 0 and total != n_rows:   # host-only check: inconsistent metadata would index past the payload
         raise RuntimeError(f'torchrua_b200: PackedSequence has {n_rows} rows of data but batch_sizes sums to {total}')
     # B counts every sequence, including empty ones that never show up in batch_sizes
-    B = unsorted_indices.numel() if unsorted_indices is not None else (int(bs_cpu[0]) if Tp > 0 else 0)
+    B = unsorted_indices.numel() if unsorted_indices is not None else (int(host[0]) if Tp > 0 else 0)
     with _on(device):
-        # one H2D for [batch_sizes | poff]
-        host = torch.empty(2 * Tp + 1, dtype=torch.long)
-        host[:Tp] = bs_cpu
-        host[Tp] = 0
-        torch.cumsum(bs_cpu, dim=0, out=host[Tp + 1:])
-        devbuf = upload(host, device)
-        bs_dev, poff = devbuf[:Tp], devbuf[Tp:]
+        devbuf = pinned.to(device, non_blocking=True)
+        bs_dev, poff = devbuf.narrow(0, 0, Tp), devbuf.narrow(0, Tp, Tp + 1)
         if unsorted_indices is None:   # enforce_sorted=True packs carry no permutation: identity
             unsorted = torch.arange(B, dtype=torch.long, device=device)
             srt = unsorted
@@ -466,7 +493,7 @@ def ragged_from_pack(batch_sizes: Tensor, sorted_indices: Optional[Tensor], unso
         require_cuda(unsorted, srt)
     # lengths of the P (one binary search per sequence) and their prefix sum in ONE launch
     off, stats, _, lens = scan(None, pack=(bs_dev, unsorted, Tp, B))
-    rg = Ragged(device=device, B=B, len=lens, off=off, stats=stats, _N=int(host[-1]) if Tp else 0, _T=Tp,
+    rg = Ragged(device=device, B=B, len=lens, off=off, stats=stats, _N=total, _T=Tp,
                 sorted=srt, unsorted=unsorted, bs_dev=bs_dev, poff=poff, bs_cpu=batch_sizes, Tp=Tp)
     rg._keep.append(devbuf)
     _cache_put(key, 'pack', rg)

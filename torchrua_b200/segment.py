@@ -1,7 +1,8 @@
 """`.seg(duration, fn)` -- mirror of torchrua/segment.py: reduce each sequence over sub-segments whose
 sizes are themselves a ragged sequence.  Thin dispatcher; the work is in the native conversions of
-``duration`` and in one native ``fn`` call.  P.seg with one of this package's own reducers skips the P -> C pass:
-the reduce kernel gathers the packed rows in sequence order itself ("seg(mean) -> pooling")."""
+``duration`` and in one native ``fn`` call.  With one of this package's own reducers the payload is read once, from
+where it lies: P.seg skips the P -> C pass and L.seg / R.seg (sum / mean / prod) skip the padding -- the reduce kernel
+gathers the packed / padded storage rows in sequence order itself ("seg(mean) -> pooling")."""
 import torch
 
 from torchrua_b200 import _native, reduce as _reduce

@@ -35,7 +35,7 @@ except Exception:
 def timed(fn, reps, clear=True):
     """median (api_ms, kernel_ms) of fn()."""
     api, ker = [], []
-    for it in range(reps + 2):
+    for it in range(reps + WARMUPS):
         if clear:
             _native._CACHE.clear()
         _native.PROFILE = []
@@ -47,13 +47,14 @@ def timed(fn, reps, clear=True):
         torch.cuda.synchronize()
         prof, _native.PROFILE = _native.PROFILE, None
         del out
-        if it >= 2:
+        if it >= WARMUPS:
             api.append(a.elapsed_time(b))
             ker.append(sum(s.elapsed_time(e) for _, s, e, _ in prof) if prof else float('nan'))
     return statistics.median(api), statistics.median(ker)
 
 
 QUIET = False
+WARMUPS = 5     # median of >= 20 timed calls after >= 5 warm-ups (--reps 20 is the default)
 ONLY = None      # --only: time just the rows whose name contains one of these substrings
 
 
@@ -302,7 +303,7 @@ def cfg5(results, reps, quiet=False):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--cfg', type=int, nargs='+', default=[2, 3, 5])
-    ap.add_argument('--reps', type=int, default=10)
+    ap.add_argument('--reps', type=int, default=20)
     ap.add_argument('--out', default=None)
     ap.add_argument('--only', nargs='+', default=None, help='substrings of the row names to time')
     args = ap.parse_args()
